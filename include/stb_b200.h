@@ -1,0 +1,59 @@
+/*
+ * stb_b200.h -- batched / device-side extensions of the stable.h API.
+ *
+ * The reference's API is scalar host calls (lib/stable.h:128-190); these entry points are the
+ * batched forms of the same look-ups, for callers that want thousands of cells at once
+ * without walking the host mirror, plus a few introspection helpers used by the tests and the
+ * benchmark.  Everything here is plain C ABI: pointers, sizes, no CUDA or torch types.
+ */
+#ifndef STB_B200_H
+#define STB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "stable.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/*
+ * out[i] = S_S(sp, n[i], m[i])  (resp. S_V) for i < count, evaluated by one gather kernel.
+ * HOST pointers; the table is first grown to cover the batch exactly as the scalar calls
+ * would (lib/stable.c:950-965), pairs beyond maxN/maxM answer -inf (S) / 0 (V); the
+ * S_ASYMPT and S_QUITONBOUND behaviours of the scalar calls are not applied.
+ * Returns non-zero on error (no such table, CUDA failure).
+ */
+int stb_S_batch(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out, size_t count);
+int stb_V_batch(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out, size_t count);
+
+/* same, n/m/out are DEVICE pointers on the table's device; no growth is attempted */
+int stb_S_batch_device(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out, size_t count);
+int stb_V_batch_device(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out, size_t count);
+
+/*
+ * Grow the filled extent to at least n<=N, m<=M (within maxN/maxM) -- the exported form of
+ * the reference's static S_extend (lib/stable.c:564), same growth policy.  0 on success.
+ */
+int stb_extend(stable_t *sp, unsigned N, unsigned M);
+
+/*
+ * Bulk export: copy rows n0 .. n0+nrows-1 (1-based) of the S (which_V==0) or V table into
+ * dst as doubles, row pitch = the slab's ld (see stb_device_table); dst holds nrows*ld
+ * doubles.  Only cells with 1<=m<=min(n,usedM) are meaningful.  0 on success.
+ */
+int stb_read_rows(stable_t *sp, int which_V, unsigned n0, unsigned nrows, double *dst);
+
+/* device milliseconds of the most recent fill (CUDA events around the kernel) */
+double stb_last_fill_ms(const stable_t *sp);
+/* device address and row pitch (elements) of the S (which_V==0) or V slab; cell (n,m) at [(n-1)*ld+m-1] */
+const void *stb_device_table(const stable_t *sp, int which_V, size_t *ld);
+/* usable CUDA devices; 0 means every S_make will fail (there is no CPU path) */
+int stb_device_count(void);
+const char *stb_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

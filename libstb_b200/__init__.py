@@ -1,0 +1,144 @@
+"""libstb_b200 -- B200-native generalised Stirling-number engine (stable.h drop-in).
+
+The product is the C-ABI shared library ``libstb_b200/lib/libstb_b200.so`` (C host layer +
+hand-written sm_100a CUDA kernels).  This Python module is only the ctypes binding the tests
+and the benchmark use to call that C ABI -- there is no Python or CPU implementation of the
+table fill here, and importing it without the built library fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libstb_b200.so")
+
+# flag bits, include/stable.h
+S_STABLE, S_UVTABLE, S_FLOAT, S_VERBOSE, S_QUITONBOUND, S_THREADS, S_ASYMPT = 1, 2, 4, 8, 16, 32, 64
+S_MIRROR_ORDER, S_NOMIRROR = 1 << 16, 1 << 17
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the C-ABI library and declare every prototype of include/*.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no CPU fallback."
+        )
+    L = C.CDLL(LIB_PATH)
+    u, d, vp, u32p, dp = C.c_uint, C.c_double, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_double)
+    L.S_make.restype, L.S_make.argtypes = vp, [u, u, u, u, d, C.c_uint32]
+    L.S_tag.restype, L.S_tag.argtypes = None, [vp, C.c_char_p]
+    L.S_remake.restype, L.S_remake.argtypes = C.c_int, [vp, d]
+    L.S_free.restype, L.S_free.argtypes = None, [vp]
+    for name in ("S_S", "S_U", "S_UV", "S_V", "S_asympt"):
+        f = getattr(L, name)
+        f.restype, f.argtypes = d, [vp, u, u]
+    L.S_S1.restype, L.S_S1.argtypes = d, [vp, u]
+    L.S_report.restype, L.S_report.argtypes = None, [vp, vp]
+    for name in ("stb_S_batch", "stb_V_batch"):
+        f = getattr(L, name)
+        f.restype, f.argtypes = C.c_int, [vp, u32p, u32p, dp, C.c_size_t]
+    for name in ("stb_S_batch_device", "stb_V_batch_device"):
+        f = getattr(L, name)
+        f.restype, f.argtypes = C.c_int, [vp, vp, vp, vp, C.c_size_t]
+    L.stb_extend.restype, L.stb_extend.argtypes = C.c_int, [vp, u, u]
+    L.stb_read_rows.restype, L.stb_read_rows.argtypes = C.c_int, [vp, C.c_int, u, u, dp]
+    L.stb_last_fill_ms.restype, L.stb_last_fill_ms.argtypes = d, [vp]
+    L.stb_device_table.restype, L.stb_device_table.argtypes = vp, [vp, C.c_int, C.POINTER(C.c_size_t)]
+    L.stb_device_count.restype, L.stb_device_count.argtypes = C.c_int, []
+    L.stb_last_error.restype, L.stb_last_error.argtypes = C.c_char_p, []
+    _lib = L
+    return L
+
+
+class _Header(C.Structure):
+    """Leading public fields of stable_t (include/stable.h)."""
+
+    _fields_ = [
+        ("maxM", C.c_uint), ("maxN", C.c_uint), ("usedM", C.c_uint), ("usedN", C.c_uint),
+        ("usedN1", C.c_uint), ("S1", C.POINTER(C.c_double)), ("lga", C.c_double), ("a", C.c_double),
+        ("flags", C.c_uint32), ("memalloced", C.c_uint32),
+    ]
+
+
+class Table:
+    """A stable_t handle.  Every method is one C-ABI call."""
+
+    def __init__(self, initN, initM, maxN=None, maxM=None, a=0.5, flags=S_STABLE | S_UVTABLE):
+        L = lib()
+        self._L = L
+        self.sp = L.S_make(initN, initM, maxN or initN, maxM or initM, a, flags)
+        if not self.sp:
+            raise RuntimeError("S_make failed: " + L.stb_last_error().decode())
+        self.flags = flags
+
+    # -- scalar API ------------------------------------------------------------------------
+    def S(self, n, m): return self._L.S_S(self.sp, n, m)
+    def V(self, n, m): return self._L.S_V(self.sp, n, m)
+    def U(self, n, m): return self._L.S_U(self.sp, n, m)
+    def UV(self, n, m): return self._L.S_UV(self.sp, n, m)
+    def S1(self, n): return self._L.S_S1(self.sp, n)
+    def asympt(self, n, m): return self._L.S_asympt(self.sp, n, m)
+
+    def remake(self, a):
+        if self._L.S_remake(self.sp, a):
+            raise RuntimeError("S_remake failed: " + self._L.stb_last_error().decode())
+
+    def extend(self, N, M):
+        if self._L.stb_extend(self.sp, N, M):
+            raise RuntimeError("stb_extend failed: " + self._L.stb_last_error().decode())
+
+    @property
+    def hdr(self): return _Header.from_address(self.sp)
+    @property
+    def usedN(self): return self.hdr.usedN
+    @property
+    def usedM(self): return self.hdr.usedM
+    @property
+    def last_fill_ms(self): return self._L.stb_last_fill_ms(self.sp)
+
+    @property
+    def ld(self):
+        ld = C.c_size_t()
+        self._L.stb_device_table(self.sp, 0, C.byref(ld))
+        return ld.value
+
+    # -- batched API -----------------------------------------------------------------------
+    def _batch(self, fn, n, m):
+        n = np.ascontiguousarray(n, dtype=np.uint32)
+        m = np.ascontiguousarray(m, dtype=np.uint32)
+        out = np.empty(n.shape[0], dtype=np.float64)
+        u32p, dp = C.POINTER(C.c_uint32), C.POINTER(C.c_double)
+        if fn(self.sp, n.ctypes.data_as(u32p), m.ctypes.data_as(u32p), out.ctypes.data_as(dp), n.shape[0]):
+            raise RuntimeError("batch look-up failed: " + self._L.stb_last_error().decode())
+        return out
+
+    def S_batch(self, n, m): return self._batch(self._L.stb_S_batch, n, m)
+    def V_batch(self, n, m): return self._batch(self._L.stb_V_batch, n, m)
+
+    def rows(self, which_V, n0, nrows):
+        """Rows n0..n0+nrows-1 as an (nrows, ld) float64 array; column j holds m=j+1."""
+        ld = self.ld
+        out = np.empty((nrows, ld), dtype=np.float64)
+        if self._L.stb_read_rows(self.sp, int(which_V), n0, nrows, out.ctypes.data_as(C.POINTER(C.c_double))):
+            raise RuntimeError("stb_read_rows failed: " + self._L.stb_last_error().decode())
+        return out
+
+    def free(self):
+        if self.sp:
+            self._L.S_free(self.sp)
+            self.sp = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

@@ -1,0 +1,507 @@
+/*
+ * stable.c -- C host layer of the Stirling table engine: the stable.h API over device tables.
+ *
+ * Mirrors the behaviour of the reference's lib/stable.c (cited per function) but owns no
+ * arithmetic on table cells: every cell is produced by the CUDA kernels behind stb_cuda.h.
+ * What lives here is the reference's control logic -- bounds clamping, the growth policy,
+ * look-up conventions, the asymptote, the S1 cache, reporting -- plus the host mirror that
+ * keeps scalar look-ups O(1).
+ *
+ * Deliberate deviations from the reference (documented in DESIGN.md):
+ *  - S_extend: the reference caps the new M at the OLD usedN (lib/stable.c:627-629), which
+ *    leaves a request with m > old usedN un-served and reads out of bounds afterwards; here
+ *    M is capped at the NEW N, so the request is served.
+ *  - S_S1: when a request grows the S1 cache the reference overwrites its own argument with
+ *    the grown size and answers for that row instead (lib/stable.c:845-872); here the answer
+ *    is always for the row that was asked.
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "stable.h"
+#include "stb_b200.h"
+#include "stb_cuda.h"
+#include "yaps.h"
+
+/* rows per lazily fetched mirror block are chosen so that a block is about this many bytes */
+#define MIRROR_BLOCK_BYTES (4u << 20)
+/* default limit (bytes of doubles, per table) under which the whole table is mirrored eagerly */
+#define MIRROR_EAGER_DEFAULT (1ull << 30)
+
+struct stb_table_impl {
+  stb_dev_t *dev;
+  int algo;
+  size_t ld; /* elements per row, device and mirror alike */
+  /* eager mirrors: [usedN][ld] doubles in pinned memory (NULL when lazy) */
+  double *fullS, *fullV;
+  size_t full_elems;
+  /* lazy mirrors: one pinned block of blk_rows rows per slot, fetched on first touch */
+  unsigned blk_rows, nblk;
+  double **blkS, **blkV;
+  pthread_mutex_t mutex;
+  int locking;
+};
+
+static void lock(stable_t *sp) {
+  if (sp->impl->locking) pthread_mutex_lock(&sp->impl->mutex);
+}
+static void unlock(stable_t *sp) {
+  if (sp->impl->locking) pthread_mutex_unlock(&sp->impl->mutex);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* host mirror                                                                                 */
+/* ------------------------------------------------------------------------------------------ */
+static void mirror_drop(stable_t *sp) {
+  struct stb_table_impl *im = sp->impl;
+  unsigned b;
+  stb_cuda_host_free(im->fullS);
+  stb_cuda_host_free(im->fullV);
+  im->fullS = im->fullV = NULL;
+  im->full_elems = 0;
+  for (b = 0; b < im->nblk; b++) {
+    if (im->blkS && im->blkS[b]) stb_cuda_host_free(im->blkS[b]);
+    if (im->blkV && im->blkV[b]) stb_cuda_host_free(im->blkV[b]);
+  }
+  free(im->blkS);
+  free(im->blkV);
+  im->blkS = im->blkV = NULL;
+  im->nblk = 0;
+}
+
+static uint64_t mirror_eager_limit(void) {
+  const char *s = getenv("STB_MIRROR_EAGER_BYTES");
+  if (s && *s) return strtoull(s, NULL, 10);
+  return MIRROR_EAGER_DEFAULT;
+}
+
+/* (re)build the mirror bookkeeping after the device tables were (re)filled; 0 on success */
+static int mirror_reset(stable_t *sp) {
+  struct stb_table_impl *im = sp->impl;
+  const int hasS = (sp->flags & S_STABLE) != 0, hasV = (sp->flags & S_UVTABLE) != 0;
+  size_t elems;
+  mirror_drop(sp);
+  im->ld = stb_cuda_table_ld(im->dev);
+  elems = (size_t)sp->usedN * im->ld;
+  if (!(sp->flags & S_NOMIRROR) && (uint64_t)elems * sizeof(double) <= mirror_eager_limit()) {
+    if (hasS) {
+      im->fullS = (double *)stb_cuda_host_alloc(elems * sizeof(double));
+      if (!im->fullS || stb_cuda_read_rows(im->dev, STB_TAB_S, 0, sp->usedN, im->fullS)) return 1;
+    }
+    if (hasV) {
+      im->fullV = (double *)stb_cuda_host_alloc(elems * sizeof(double));
+      if (!im->fullV || stb_cuda_read_rows(im->dev, STB_TAB_V, 0, sp->usedN, im->fullV)) return 1;
+    }
+    im->full_elems = elems;
+    return 0;
+  }
+  im->blk_rows = (unsigned)(MIRROR_BLOCK_BYTES / (im->ld * sizeof(double)));
+  if (im->blk_rows < 1) im->blk_rows = 1;
+  im->nblk = (sp->usedN + im->blk_rows - 1) / im->blk_rows;
+  if (hasS && !(im->blkS = (double **)calloc(im->nblk, sizeof(double *)))) return 1;
+  if (hasV && !(im->blkV = (double **)calloc(im->nblk, sizeof(double *)))) return 1;
+  return 0;
+}
+
+/* slow path of a lazy read: bring one block of rows across; NULL on failure */
+static double *mirror_fetch(stable_t *sp, int which, unsigned b) {
+  struct stb_table_impl *im = sp->impl;
+  double **tab = which == STB_TAB_S ? im->blkS : im->blkV;
+  double *blk;
+  lock(sp);
+  blk = tab[b];
+  if (!blk) {
+    unsigned row0 = b * im->blk_rows, rows = im->blk_rows;
+    if (row0 + rows > sp->usedN) rows = sp->usedN - row0;
+    blk = (double *)stb_cuda_host_alloc((size_t)im->blk_rows * im->ld * sizeof(double));
+    if (blk && stb_cuda_read_rows(im->dev, which, row0, rows, blk)) {
+      stb_cuda_host_free(blk);
+      blk = NULL;
+    }
+    /* publish only after the block is complete: readers are lock-free */
+    __atomic_store_n(&tab[b], blk, __ATOMIC_RELEASE);
+  }
+  unlock(sp);
+  return blk;
+}
+
+/* cell (n,m), 1<=m<=n<=usedN, m<=usedM */
+static double cell(stable_t *sp, int which, unsigned n, unsigned m) {
+  struct stb_table_impl *im = sp->impl;
+  const double *full = which == STB_TAB_S ? im->fullS : im->fullV;
+  if (full) return full[(size_t)(n - 1) * im->ld + (m - 1)];
+  {
+    double **tab = which == STB_TAB_S ? im->blkS : im->blkV;
+    unsigned b = (n - 1) / im->blk_rows;
+    double *blk = __atomic_load_n(&tab[b], __ATOMIC_ACQUIRE);
+    if (!blk && !(blk = mirror_fetch(sp, which, b)))
+      yaps_quit("stable: device read failed: %s\n", stb_cuda_last_error());
+    return blk[(size_t)((n - 1) % im->blk_rows) * im->ld + (m - 1)];
+  }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* fill                                                                                        */
+/* ------------------------------------------------------------------------------------------ */
+/*
+ * Fill the device tables for rows<=N, cols<=M at discount a and refresh S1 + mirror.
+ * Counterpart of S_remake_part (lib/stable.c:321-547); bounds are published last (:543-545).
+ */
+static int fill(stable_t *sp, double a, unsigned startN, unsigned startM, unsigned N, unsigned M) {
+  struct stb_table_impl *im = sp->impl;
+  const int hasS = (sp->flags & S_STABLE) != 0;
+  const int mirror_order = im->algo == STB_FILL_MIRROR;
+  unsigned n;
+  sp->a = a;
+  sp->lga = lgamma(1.0 - a);
+  if (mirror_order || !hasS) {
+    /* S1 running sum in the reference's order, lib/stable.c:338-348 */
+    sp->S1[0] = 0;
+    for (n = 2; n <= N; n++) sp->S1[n - 1] = sp->S1[n - 2] + log(n - 1 - a);
+  }
+  if (stb_cuda_fill(im->dev, a, startN, startM, N, M, im->algo,
+                    (mirror_order || hasS) ? sp->S1 : NULL))
+    return 1;
+  /* a changed: forget the lazily computed tail of S1, lib/stable.c:350-353 */
+  for (n = N + 1; n <= sp->usedN1; n++) sp->S1[n - 1] = 0;
+  sp->usedN = N;
+  sp->usedM = M;
+  return mirror_reset(sp);
+}
+
+stable_t *S_make(unsigned initN, unsigned initM, unsigned maxN, unsigned maxM, double a, uint32_t flags) {
+  stable_t *sp;
+  struct stb_table_impl *im;
+  /* lib/stable.c:118-129 */
+  if (maxM < 10) maxM = 10;
+  if (maxN < maxM) maxN = maxM;
+  if (initM < 10) initM = 10;
+  if (initN < initM) initN = initM;
+  if (initN > maxN) initN = maxN;
+  if (initM > maxM) initM = maxM;
+  /* lib/stable.c:131-132 */
+  if ((flags & S_STABLE) == 0 && (flags & S_UVTABLE) == 0) return NULL;
+
+  sp = (stable_t *)calloc(1, sizeof *sp);
+  im = (struct stb_table_impl *)calloc(1, sizeof *im);
+  if (!sp || !im) {
+    free(sp);
+    free(im);
+    return NULL;
+  }
+  sp->impl = im;
+  sp->flags = flags;
+  sp->maxN = maxN;
+  sp->maxM = maxM;
+  sp->usedN = initN;
+  sp->usedM = initM;
+  sp->usedN1 = initN;
+  pthread_mutex_init(&im->mutex, NULL);
+  im->locking = (flags & S_THREADS) != 0;
+  im->algo = (flags & S_MIRROR_ORDER) ? STB_FILL_MIRROR : STB_FILL_LINEAR;
+  {
+    const char *s = getenv("STB_FILL_ALGO");
+    if (s && !strcmp(s, "mirror")) im->algo = STB_FILL_MIRROR;
+    if (s && !strcmp(s, "linear")) im->algo = STB_FILL_LINEAR;
+  }
+  sp->S1 = (double *)calloc(initN, sizeof(double));
+  im->dev = stb_cuda_table_create((flags & S_STABLE) != 0, (flags & S_UVTABLE) != 0, (flags & S_FLOAT) != 0);
+  if (!sp->S1 || !im->dev || stb_cuda_table_reserve(im->dev, initN, initM, 0) ||
+      fill(sp, a, 0, 0, initN, initM)) {
+    if (stb_cuda_last_error()[0]) yaps_message("S_make: %s\n", stb_cuda_last_error());
+    S_free(sp);
+    return NULL;
+  }
+  if (flags & S_VERBOSE) S_report(sp, stderr);
+  return sp;
+}
+
+void S_tag(stable_t *S, char *tag) {
+  free(S->tag);
+  S->tag = (char *)malloc(strlen(tag) + 1);
+  if (S->tag) strcpy(S->tag, tag);
+}
+
+int S_remake(stable_t *sp, double a) {
+  int ret = fill(sp, a, 0, 0, sp->usedN, sp->usedM);
+  if (!ret && (sp->flags & S_VERBOSE)) S_report(sp, stderr);
+  return ret;
+}
+
+/*
+ * Growth, lib/stable.c:564-815: a request for (N,M) grows each dimension by at least 10% and
+ * at least 50, capped by the maxima.  Returns non-zero when memory (host or device) ran out.
+ */
+static int extend(stable_t *sp, unsigned Nreq, unsigned Mreq) {
+  struct stb_table_impl *im = sp->impl;
+  long N = (long)Nreq + 1, M = (long)Mreq + 1;
+  int result = 0;
+  lock(sp);
+  if (N < (long)sp->usedN && M < (long)sp->usedM) goto done; /* someone else already grew it */
+  if (N < (long)sp->usedN) N = sp->usedN;
+  if (N > (long)sp->maxN) N = sp->maxN;
+  if (N > (long)sp->usedN) {
+    if (N < sp->usedN * 1.1) N = (long)(sp->usedN * 1.1);
+    if (N < (long)sp->usedN + 50) N = (long)sp->usedN + 50;
+    if (N > (long)sp->maxN) N = sp->maxN;
+  }
+  if (M < (long)sp->usedM) M = sp->usedM;
+  if (N < M) M = N;
+  if (M > (long)sp->maxM) M = sp->maxM;
+  if (M > (long)sp->usedM) {
+    if (M < sp->usedM * 1.1) M = (long)(sp->usedM * 1.1);
+    if (M < (long)sp->usedM + 50) M = (long)sp->usedM + 50;
+    if (M > (long)sp->maxM) M = sp->maxM;
+    if (M > N) M = N; /* deviation: the reference caps at the old usedN */
+  }
+  if (N == (long)sp->usedN && M == (long)sp->usedM) goto done;
+  if (N > (long)sp->usedN1) {
+    double *s1 = (double *)realloc(sp->S1, sizeof(double) * (size_t)N);
+    if (!s1) {
+      result = 1;
+      goto done;
+    }
+    memset(s1 + sp->usedN1, 0, sizeof(double) * (size_t)(N - sp->usedN1));
+    sp->S1 = s1;
+    sp->usedN1 = (unsigned)N;
+  }
+  if (stb_cuda_table_reserve(im->dev, (unsigned)N, (unsigned)M, 1) ||
+      fill(sp, sp->a, sp->usedN, sp->usedM, (unsigned)N, (unsigned)M))
+    result = 1;
+done:
+  unlock(sp);
+  return result;
+}
+
+/* lib/stable.c:822-873 */
+double S_S1(stable_t *sp, unsigned n) {
+  if (n == 0) return -HUGE_VAL;
+  if (!sp->S1) return -HUGE_VAL;
+  if (n > sp->usedN) {
+    double v;
+    if (n > sp->maxN) {
+      if (!(sp->flags & S_ASYMPT)) return -HUGE_VAL;
+      /* past the bound the closed form is exact for m==1 */
+      return lgamma(n - sp->a) - sp->lga;
+    }
+    lock(sp);
+    if (n > sp->usedN1) {
+      unsigned want = n;
+      double *s1;
+      if (want < sp->usedN1 * 1.1) want = (unsigned)(sp->usedN1 * 1.1);
+      if (want < sp->usedN1 + 50) want = sp->usedN1 + 50;
+      if (want > sp->maxN) want = sp->maxN;
+      s1 = (double *)realloc(sp->S1, sizeof(double) * want);
+      if (!s1) {
+        unlock(sp);
+        return -HUGE_VAL;
+      }
+      memset(s1 + sp->usedN1, 0, sizeof(double) * (want - sp->usedN1));
+      sp->S1 = s1;
+      sp->usedN1 = want;
+    }
+    if (sp->S1[n - 1] == 0) {
+      if (sp->S1[n - 2] == 0)
+        sp->S1[n - 1] = lgamma(n - sp->a) - sp->lga;
+      else
+        sp->S1[n - 1] = sp->S1[n - 2] + log(n - 1 - sp->a);
+    }
+    v = sp->S1[n - 1];
+    unlock(sp);
+    return v;
+  }
+  return sp->S1[n - 1];
+}
+
+/* lib/stable.c:875-883 */
+double S_U(stable_t *sp, unsigned n, unsigned m) {
+  if (m == 1) return n - sp->a;
+  if (m <= 1) yaps_quit("Bad constraints in S_U(%s,%u,%u)\n", sp->tag, n, m);
+  return n - m * sp->a + 1 / S_V(sp, n, m);
+}
+
+/* lib/stable.c:885-897 */
+double S_UV(stable_t *sp, unsigned n, unsigned m) {
+  double SV;
+  if (m == 1) return -HUGE_VAL;
+  if (m == n + 1) return 1; /* S^n_n == 1 */
+  if (m == n) return (n + 1.0) / (n - 1.0);
+  SV = S_V(sp, n, m);
+  return (n - m * sp->a) * SV + 1.0;
+}
+
+/* the V asymptote, lib/stable.c:905-911 */
+static double v_asympt(stable_t *sp, unsigned n, unsigned m) {
+  if (sp->a > 0) return (1.0 - pow(n, -sp->a)) / sp->a / (m - 1);
+  {
+    double ln = log(n);
+    return ln / (m - 1) * exp(lgamma(1 + (m - 2) / ln) - lgamma(1 + (m - 1) / ln));
+  }
+}
+
+/* lib/stable.c:900-939 */
+double S_V(stable_t *sp, unsigned n, unsigned m) {
+  if ((sp->flags & S_UVTABLE) == 0) return 0;
+  if (m + 1 >= sp->usedM || n + 1 >= sp->usedN) {
+    if (n > sp->maxN || m > sp->maxM) {
+      if (n > sp->maxN && (sp->flags & S_ASYMPT)) return v_asympt(sp, n, m);
+      if (sp->flags & S_QUITONBOUND) {
+        if (sp->tag)
+          yaps_quit("S_V(%u,%u,%lf) tagged '%s' hit bounds (%u,%u)\n", n, m, sp->a, sp->tag, sp->maxN,
+                    sp->maxM);
+        else
+          yaps_quit("S_V(%u,%u,%lf) hit bounds\n", n, m, sp->a);
+      } else
+        return 0;
+    }
+    if (extend(sp, n + 1, m + 1)) yaps_quit("S_extend() out of memory\n");
+  }
+  if (m < 2 || n < m) return 0;
+  return cell(sp, STB_TAB_V, n, m);
+}
+
+/* lib/stable.c:941-974 */
+double S_S(stable_t *sp, unsigned N, unsigned T) {
+  if ((sp->flags & S_STABLE) == 0) return -HUGE_VAL;
+  if (N == T) return 0;
+  if (T == 1) return S_S1(sp, N);
+  if (N < T || T == 0) return -HUGE_VAL;
+  if (T > sp->usedM || N > sp->usedN) {
+    if (N > sp->maxN || T > sp->maxM) {
+      if (N > sp->maxN && (sp->flags & S_ASYMPT)) return S_asympt(sp, N, T);
+      if (sp->flags & S_QUITONBOUND) {
+        if (sp->tag)
+          yaps_quit("S_S(%u,%u,%lf) tagged '%s' hit bounds\n", N, T, sp->a, sp->tag);
+        else
+          yaps_quit("S_S(%u,%u,%lf) hit bounds\n", N, T, sp->a);
+      } else
+        return -HUGE_VAL;
+    }
+    if (extend(sp, N + 1, T + 1)) yaps_quit("S_extend() out of memory\n");
+  }
+  return cell(sp, STB_TAB_S, N, T);
+}
+
+/* lib/stable.c:980-1023 */
+void S_free(stable_t *sp) {
+  if (!sp) return;
+  if (sp->impl) {
+    mirror_drop(sp);
+    stb_cuda_table_destroy(sp->impl->dev);
+    pthread_mutex_destroy(&sp->impl->mutex);
+    free(sp->impl);
+  }
+  free(sp->tag);
+  free(sp->S1);
+  free(sp);
+}
+
+/* lib/stable.c:1025-1055: same one-line format, including the trailing blank line */
+void S_report(stable_t *sp, FILE *fp) {
+  const char *s = (sp->flags & S_STABLE) ? "+S" : "", *uv = (sp->flags & S_UVTABLE) ? "+U/V" : "";
+  const char *ty = (sp->flags & S_FLOAT) ? "float" : "double";
+  uint64_t bytes = stb_cuda_table_bytes(sp->impl->dev) + (uint64_t)sp->usedN1 * sizeof(double) +
+                   (uint64_t)sp->impl->full_elems * sizeof(double) *
+                       (((sp->flags & S_STABLE) != 0) + ((sp->flags & S_UVTABLE) != 0));
+  sp->memalloced = (uint32_t)bytes; /* the reference keeps a uint32 too (lib/stable.h:105) */
+  if (fp) {
+    if (sp->tag)
+      fprintf(fp, "S-table '%s': ", sp->tag);
+    else
+      fprintf(fp, "S-table: ");
+    fprintf(fp, "a=%lf, N=%u/%u, M=%u/%u, %s%s %s", sp->a, sp->usedN, sp->maxN, sp->usedM, sp->maxM, s, uv, ty);
+    fprintf(fp, " mem=%uk\n", sp->memalloced / 1024);
+    fprintf(fp, "\n");
+  } else {
+    if (sp->tag)
+      yaps_message("S-table '%s': ", sp->tag);
+    else
+      yaps_message("S-table: ");
+    yaps_message("a=%lf, N=%u/%u, M=%u/%u, %s%s %s", sp->a, sp->usedN, sp->maxN, sp->usedM, sp->maxM, s, uv, ty);
+    yaps_message(" mem=%uk", sp->memalloced / 1024);
+    yaps_message("\n");
+  }
+}
+
+/*
+ * lib/stable.c:1057-1084.  a>0: Hutter's form  Gamma(n) / (Gamma(1-a) Gamma(m) a^{m-1} n^a)
+ * times (1-n^{-a})^{m-1}; a==0: Hwang's expansion for Stirling numbers of the first kind.
+ */
+double S_asympt(stable_t *sp, unsigned n, unsigned m) {
+  if (sp->a == 0) {
+    double ln = log(n);
+    return lgamma(n) + (m - 1) * log(ln) - lgamma(m) - lgamma(1 + (m - 1) / ln);
+  } else {
+    double prod = 0;
+    double la1 = lgamma(1.0 - sp->a);
+    double aln = sp->a * log((double)n);
+    double np = pow(n, -sp->a);
+    prod += lgamma((double)n) - la1 - lgamma((double)m) - (m - 1.0) * log(sp->a) - aln;
+    if (np < 1e-5)
+      prod -= (m - 1) * np * (1 + np * (0.5 + np / 3.0));
+    else
+      prod += (m - 1) * log(1.0 - np);
+    return prod;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* batched extensions (stb_b200.h)                                                             */
+/* ------------------------------------------------------------------------------------------ */
+static int batch(stable_t *sp, int which, const uint32_t *n, const uint32_t *m, double *out, size_t count,
+                 int on_device) {
+  if (!sp || !sp->impl) return 1;
+  if (which == STB_TAB_S && !(sp->flags & S_STABLE)) return 1;
+  if (which == STB_TAB_V && !(sp->flags & S_UVTABLE)) return 1;
+  if (!on_device) {
+    /* grow once to cover the whole batch, like the scalar calls would one by one */
+    unsigned maxn = 0, maxm = 0;
+    size_t i;
+    for (i = 0; i < count; i++) {
+      if (n[i] >= m[i] && n[i] <= sp->maxN && m[i] <= sp->maxM) {
+        if (n[i] > maxn) maxn = n[i];
+        if (m[i] > maxm) maxm = m[i];
+      }
+    }
+    if (maxn > sp->usedN || maxm > sp->usedM)
+      if (extend(sp, maxn > sp->usedN ? maxn : sp->usedN, maxm > sp->usedM ? maxm : sp->usedM)) return 1;
+  }
+  return stb_cuda_gather(sp->impl->dev, which, sp->usedN, sp->usedM, n, m, out, count, on_device);
+}
+
+int stb_S_batch(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out, size_t count) {
+  return batch(sp, STB_TAB_S, n, m, out, count, 0);
+}
+int stb_V_batch(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out, size_t count) {
+  return batch(sp, STB_TAB_V, n, m, out, count, 0);
+}
+int stb_S_batch_device(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out, size_t count) {
+  return batch(sp, STB_TAB_S, n, m, out, count, 1);
+}
+int stb_V_batch_device(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out, size_t count) {
+  return batch(sp, STB_TAB_V, n, m, out, count, 1);
+}
+
+int stb_extend(stable_t *sp, unsigned N, unsigned M) {
+  if (!sp || N > sp->maxN || M > sp->maxM) return 1;
+  if (N <= sp->usedN && M <= sp->usedM) return 0;
+  return extend(sp, N > sp->usedN ? N : sp->usedN, M > sp->usedM ? M : sp->usedM);
+}
+
+int stb_read_rows(stable_t *sp, int which_V, unsigned n0, unsigned nrows, double *dst) {
+  if (!sp || n0 < 1 || n0 + nrows - 1 > sp->usedN) return 1;
+  if (which_V ? !(sp->flags & S_UVTABLE) : !(sp->flags & S_STABLE)) return 1;
+  return stb_cuda_read_rows(sp->impl->dev, which_V ? STB_TAB_V : STB_TAB_S, n0 - 1, nrows, dst);
+}
+
+double stb_last_fill_ms(const stable_t *sp) { return stb_cuda_last_fill_ms(sp->impl->dev); }
+const void *stb_device_table(const stable_t *sp, int which_V, size_t *ld) {
+  if (ld) *ld = stb_cuda_table_ld(sp->impl->dev);
+  return stb_cuda_table_ptr(sp->impl->dev, which_V ? STB_TAB_V : STB_TAB_S);
+}
+int stb_device_count(void) { return stb_cuda_device_count(); }
+const char *stb_last_error(void) { return stb_cuda_last_error(); }

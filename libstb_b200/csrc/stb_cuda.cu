@@ -1,0 +1,323 @@
+/*
+ * stb_cuda.cu -- device-side table object and kernel launchers behind stb_cuda.h.
+ *
+ * Replaces the allocation part of S_make (lib/stable.c:155-304: ragged row pointers, one
+ * malloc per row) by ONE dense row-major slab per table in HBM, and S_remake_part's two
+ * double loops (lib/stable.c:356-388, 451-482) by the kernels in fill_linear.cuh /
+ * fill_mirror.cuh.  sm_100a only; no CPU path.
+ */
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "stb_cuda.h"
+#include "fill_mirror.cuh"
+#include "fill_linear.cuh"
+
+static char g_err[512] = "";
+
+static int fail(cudaError_t e, const char *what) {
+  snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
+  return (int)e ? (int)e : -1;
+}
+#define CK(call)                                   \
+  do {                                             \
+    cudaError_t e_ = (call);                       \
+    if (e_ != cudaSuccess) return fail(e_, #call); \
+  } while (0)
+
+struct stb_dev {
+  int device;
+  int num_sms;
+  cudaStream_t stream;
+  cudaEvent_t ev0, ev1;
+  int has_S, has_V, is_float;
+  unsigned capN, capM;  // rows / columns the slabs can hold
+  size_t ld;            // elements per row
+  void *S, *V;          // [capN][ld] of double or float
+  double *s1;           // device copy of column 1 / S1 (capN doubles)
+  double *scratch;      // mirror kernel live rows
+  size_t scratch_elems;
+  stb::LinearState lin;  // frontier state + hand-off rings of the linear kernel
+  float last_ms;
+  // staging for host-pointer gathers
+  uint32_t *g_n, *g_m;
+  double *g_out;
+  size_t g_cap;
+};
+
+extern "C" int stb_cuda_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    fail(e, "cudaGetDeviceCount");
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+extern "C" const char *stb_cuda_last_error(void) { return g_err; }
+
+extern "C" stb_dev_t *stb_cuda_table_create(int want_S, int want_V, int is_float) {
+  if (stb_cuda_device_count() <= 0) {
+    if (!g_err[0]) snprintf(g_err, sizeof g_err, "no CUDA device");
+    return NULL;
+  }
+  stb_dev_t *d = (stb_dev_t *)calloc(1, sizeof *d);
+  if (!d) return NULL;
+  d->has_S = want_S != 0;
+  d->has_V = want_V != 0;
+  d->is_float = is_float != 0;
+  if (cudaGetDevice(&d->device) != cudaSuccess ||
+      cudaDeviceGetAttribute(&d->num_sms, cudaDevAttrMultiProcessorCount, d->device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&d->ev0) != cudaSuccess || cudaEventCreate(&d->ev1) != cudaSuccess) {
+    fail(cudaGetLastError(), "stb_cuda_table_create");
+    free(d);
+    return NULL;
+  }
+  return d;
+}
+
+extern "C" void stb_cuda_table_destroy(stb_dev_t *d) {
+  if (!d) return;
+  cudaSetDevice(d->device);
+  cudaStreamSynchronize(d->stream);
+  cudaFree(d->S);
+  cudaFree(d->V);
+  cudaFree(d->s1);
+  cudaFree(d->scratch);
+  cudaFree(d->g_n);
+  cudaFree(d->g_m);
+  cudaFree(d->g_out);
+  stb::linear_state_free(&d->lin);
+  cudaEventDestroy(d->ev0);
+  cudaEventDestroy(d->ev1);
+  cudaStreamDestroy(d->stream);
+  free(d);
+}
+
+static size_t elem_size(const stb_dev_t *d) { return d->is_float ? sizeof(float) : sizeof(double); }
+
+extern "C" size_t stb_cuda_table_ld(const stb_dev_t *d) { return d->ld; }
+
+extern "C" size_t stb_cuda_table_bytes(const stb_dev_t *d) {
+  size_t slab = (size_t)d->capN * d->ld * elem_size(d);
+  return slab * (size_t)(d->has_S + d->has_V) + (size_t)d->capN * sizeof(double) +
+         d->scratch_elems * sizeof(double) + stb::linear_state_bytes(&d->lin);
+}
+
+extern "C" int stb_cuda_table_reserve(stb_dev_t *d, unsigned N, unsigned M, int keep) {
+  CK(cudaSetDevice(d->device));
+  if (N <= d->capN && M <= d->capM) return 0;
+  unsigned newN = N > d->capN ? N : d->capN;
+  unsigned newM = M > d->capM ? M : d->capM;
+  size_t newld = ((size_t)newM + 31) / 32 * 32;
+  size_t es = elem_size(d);
+  void *nS = NULL, *nV = NULL;
+  double *ns1 = NULL;
+  cudaError_t e = cudaSuccess;
+  if (d->has_S) e = cudaMalloc(&nS, (size_t)newN * newld * es);
+  if (e == cudaSuccess && d->has_V) e = cudaMalloc(&nV, (size_t)newN * newld * es);
+  if (e == cudaSuccess) e = cudaMalloc(&ns1, (size_t)newN * sizeof(double));
+  if (e != cudaSuccess) {
+    cudaFree(nS);
+    cudaFree(nV);
+    cudaFree(ns1);
+    return fail(e, "cudaMalloc(table slab)");
+  }
+  if (keep && d->capN) {
+    CK(cudaStreamSynchronize(d->stream));
+    if (d->has_S)
+      CK(cudaMemcpy2D(nS, newld * es, d->S, d->ld * es, (size_t)d->capM * es, d->capN,
+                      cudaMemcpyDeviceToDevice));
+    if (d->has_V)
+      CK(cudaMemcpy2D(nV, newld * es, d->V, d->ld * es, (size_t)d->capM * es, d->capN,
+                      cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(ns1, d->s1, (size_t)d->capN * sizeof(double), cudaMemcpyDeviceToDevice));
+  }
+  cudaFree(d->S);
+  cudaFree(d->V);
+  cudaFree(d->s1);
+  d->S = nS;
+  d->V = nV;
+  d->s1 = ns1;
+  d->capN = newN;
+  d->capM = newM;
+  d->ld = newld;
+  return 0;
+}
+
+extern "C" void *stb_cuda_table_ptr(stb_dev_t *d, int which) { return which == STB_TAB_S ? d->S : d->V; }
+
+extern "C" float stb_cuda_last_fill_ms(const stb_dev_t *d) { return d->last_ms; }
+
+static int fill_mirror(stb_dev_t *d, double a, unsigned N, unsigned M, double *s1_host) {
+  size_t need = 4 * ((size_t)M + 2);
+  if (need > d->scratch_elems) {
+    cudaFree(d->scratch);
+    d->scratch = NULL;
+    d->scratch_elems = 0;
+    CK(cudaMalloc(&d->scratch, need * sizeof(double)));
+    d->scratch_elems = need;
+  }
+  if (!s1_host) {
+    snprintf(g_err, sizeof g_err, "mirror fill needs the host S1 running sum");
+    return -1;
+  }
+  CK(cudaMemcpyAsync(d->s1, s1_host, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+  CK(cudaEventRecord(d->ev0, d->stream));
+  if (d->is_float)
+    stb::fill_mirror_kernel<float><<<1, 1024, 0, d->stream>>>((float *)d->S, (float *)d->V, d->s1,
+                                                             d->scratch, d->ld, N, M, a);
+  else
+    stb::fill_mirror_kernel<double><<<1, 1024, 0, d->stream>>>((double *)d->S, (double *)d->V, d->s1,
+                                                               d->scratch, d->ld, N, M, a);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(d->ev1, d->stream));
+  CK(cudaStreamSynchronize(d->stream));
+  CK(cudaEventElapsedTime(&d->last_ms, d->ev0, d->ev1));
+  return 0;
+}
+
+extern "C" int stb_cuda_fill(stb_dev_t *d, double a, unsigned startN, unsigned startM, unsigned N,
+                             unsigned M, int algo, double *s1_host) {
+  CK(cudaSetDevice(d->device));
+  if (N > d->capN || M > d->capM || N < 1 || M < 1) {
+    snprintf(g_err, sizeof g_err, "stb_cuda_fill: extent %ux%u exceeds reserved %ux%u", N, M, d->capN,
+             d->capM);
+    return -1;
+  }
+  if (algo == STB_FILL_MIRROR) return fill_mirror(d, a, N, M, s1_host);
+  // linear-domain strip pipeline
+  stb::LinearFillArgs args;
+  args.tabS = d->has_S ? d->S : NULL;
+  args.tabV = d->has_V ? d->V : NULL;
+  args.s1 = d->s1;
+  args.is_float = d->is_float;
+  args.ld = d->ld;
+  args.a = a;
+  args.startN = startN;
+  args.startM = startM;
+  args.N = N;
+  args.M = M;
+  args.num_sms = d->num_sms;
+  CK(cudaEventRecord(d->ev0, d->stream));
+  int rc = stb::linear_fill(&d->lin, args, d->stream, d->ev1, g_err, sizeof g_err);
+  if (rc) return rc;
+  if (s1_host && d->has_S)
+    CK(cudaMemcpyAsync(s1_host, d->s1, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+  CK(cudaStreamSynchronize(d->stream));
+  CK(cudaEventElapsedTime(&d->last_ms, d->ev0, d->ev1));
+  return 0;
+}
+
+extern "C" int stb_cuda_read_rows(stb_dev_t *d, int which, unsigned row0, unsigned nrows, double *dst) {
+  CK(cudaSetDevice(d->device));
+  const void *tab = which == STB_TAB_S ? d->S : d->V;
+  if (!tab || row0 + nrows > d->capN) {
+    snprintf(g_err, sizeof g_err, "stb_cuda_read_rows: bad range");
+    return -1;
+  }
+  size_t cnt = (size_t)nrows * d->ld;
+  if (!d->is_float) {
+    CK(cudaMemcpyAsync(dst, (const double *)tab + (size_t)row0 * d->ld, cnt * sizeof(double),
+                       cudaMemcpyDeviceToHost, d->stream));
+    CK(cudaStreamSynchronize(d->stream));
+  } else {
+    // copy the floats into the tail of dst, then widen front to back
+    float *tmp = (float *)dst + cnt;
+    CK(cudaMemcpyAsync(tmp, (const float *)tab + (size_t)row0 * d->ld, cnt * sizeof(float),
+                       cudaMemcpyDeviceToHost, d->stream));
+    CK(cudaStreamSynchronize(d->stream));
+    for (size_t i = 0; i < cnt; i++) dst[i] = (double)tmp[i];
+  }
+  return 0;
+}
+
+/*
+ * Batched look-up with the scalar API's in-range conventions (lib/stable.c:941-949, 927-928):
+ *   S: n==m -> 0, m==0 or n<m -> -inf, else the cell (m==1 is column 0 of the slab);
+ *   V: m<2 or n<m -> 0, else the cell.
+ * Anything outside the filled extent answers like "beyond bounds" (-inf / 0).
+ */
+template <typename T>
+__global__ void gather_kernel(const T *__restrict__ tab, size_t ld, int is_V, unsigned usedN, unsigned usedM,
+                              const uint32_t *__restrict__ n, const uint32_t *__restrict__ m,
+                              double *__restrict__ out, size_t count) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const unsigned nn = n[i], mm = m[i];
+  double v;
+  if (is_V) {
+    v = (mm < 2 || nn < mm || nn > usedN || mm > usedM) ? 0.0 : (double)tab[(size_t)(nn - 1) * ld + (mm - 1)];
+  } else {
+    if (nn == mm)
+      v = 0.0;
+    else if (mm == 0 || nn < mm || nn > usedN || mm > usedM)
+      v = -HUGE_VAL;
+    else
+      v = (double)tab[(size_t)(nn - 1) * ld + (mm - 1)];
+  }
+  out[i] = v;
+}
+
+extern "C" int stb_cuda_gather(stb_dev_t *d, int which, unsigned usedN, unsigned usedM, const uint32_t *n,
+                               const uint32_t *m, double *out, size_t count, int on_device) {
+  CK(cudaSetDevice(d->device));
+  const void *tab = which == STB_TAB_S ? d->S : d->V;
+  if (!tab) {
+    snprintf(g_err, sizeof g_err, "stb_cuda_gather: table not held");
+    return -1;
+  }
+  if (count == 0) return 0;
+  const uint32_t *dn = n, *dm = m;
+  double *dout = out;
+  if (!on_device) {
+    if (count > d->g_cap) {
+      cudaFree(d->g_n);
+      cudaFree(d->g_m);
+      cudaFree(d->g_out);
+      d->g_n = d->g_m = NULL;
+      d->g_out = NULL;
+      d->g_cap = 0;
+      CK(cudaMalloc(&d->g_n, count * sizeof(uint32_t)));
+      CK(cudaMalloc(&d->g_m, count * sizeof(uint32_t)));
+      CK(cudaMalloc(&d->g_out, count * sizeof(double)));
+      d->g_cap = count;
+    }
+    CK(cudaMemcpyAsync(d->g_n, n, count * sizeof(uint32_t), cudaMemcpyHostToDevice, d->stream));
+    CK(cudaMemcpyAsync(d->g_m, m, count * sizeof(uint32_t), cudaMemcpyHostToDevice, d->stream));
+    dn = d->g_n;
+    dm = d->g_m;
+    dout = d->g_out;
+  }
+  unsigned blocks = (unsigned)((count + 255) / 256);
+  if (d->is_float)
+    gather_kernel<float><<<blocks, 256, 0, d->stream>>>((const float *)tab, d->ld, which == STB_TAB_V, usedN,
+                                                        usedM, dn, dm, dout, count);
+  else
+    gather_kernel<double><<<blocks, 256, 0, d->stream>>>((const double *)tab, d->ld, which == STB_TAB_V, usedN,
+                                                         usedM, dn, dm, dout, count);
+  CK(cudaGetLastError());
+  if (!on_device)
+    CK(cudaMemcpyAsync(out, d->g_out, count * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+  CK(cudaStreamSynchronize(d->stream));
+  return 0;
+}
+
+extern "C" void *stb_cuda_host_alloc(size_t bytes) {
+  void *p = NULL;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return NULL;
+  }
+  return p;
+}
+
+extern "C" void stb_cuda_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}

@@ -1,0 +1,90 @@
+/*
+ * stb_cuda.h -- the thin C-ABI between the C host layer (stable.c, samplers.c) and the
+ * CUDA translation units.  Plain pointers and sizes only.  Every function returns 0 on
+ * success and a non-zero cudaError_t-like code on failure unless stated otherwise; the C
+ * layer maps failures onto the reference's conventions (NULL from S_make, yaps_quit on
+ * growth failure -- lib/stable.c:115-116, 924-925, 963-964).
+ *
+ * There is deliberately no CPU implementation behind any of these: without a CUDA device
+ * the calls fail and the public API reports the failure.
+ */
+#ifndef STB_CUDA_H
+#define STB_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct stb_dev stb_dev_t;
+
+/* which table */
+#define STB_TAB_S 0
+#define STB_TAB_V 1
+
+/* fill algorithms */
+#define STB_FILL_LINEAR 0 /* scaled linear-domain recurrence, strip-pipelined (default) */
+#define STB_FILL_MIRROR 1 /* reference operation order, log domain (S) / ratio recursion (V) */
+
+/* number of usable CUDA devices (0 when none / driver missing) */
+int stb_cuda_device_count(void);
+/* last CUDA error text for diagnostics (static storage) */
+const char *stb_cuda_last_error(void);
+
+/*
+ * Create the device side of one table object on the current device.
+ *   want_S / want_V : which tables to hold;  is_float : store cells as float.
+ */
+stb_dev_t *stb_cuda_table_create(int want_S, int want_V, int is_float);
+void stb_cuda_table_destroy(stb_dev_t *d);
+
+/*
+ * Make room for rows n=1..N and columns m=1..M.  Cells are laid out dense row-major: cell
+ * (n,m) at [(n-1)*ld + (m-1)], ld = M rounded up to 32 elements so that every row starts on a
+ * 128-byte boundary.  With keep!=0 the cells already filled survive a re-allocation.
+ */
+int stb_cuda_table_reserve(stb_dev_t *d, unsigned N, unsigned M, int keep);
+size_t stb_cuda_table_ld(const stb_dev_t *d);
+size_t stb_cuda_table_bytes(const stb_dev_t *d); /* device bytes currently held */
+
+/*
+ * Fill rows 1..N, columns 1..M at discount a with the chosen algorithm, then wait for
+ * completion.  Cells with n<=startN && m<=startM are declared already valid for this a
+ * (startN==0: nothing is) -- the counterpart of S_remake_part's start arguments,
+ * lib/stable.c:321-323.  Column 1 of the S table is log S^n_1; `s1_host` (N doubles, may be
+ * NULL) receives it.  With STB_FILL_MIRROR the caller instead passes the host-computed S1
+ * running sum in `s1_host` (uploaded and used as the m=1 column, lib/stable.c:338-348).
+ */
+int stb_cuda_fill(stb_dev_t *d, double a, unsigned startN, unsigned startM, unsigned N, unsigned M,
+                  int algo, double *s1_host);
+/* milliseconds the device spent in the most recent stb_cuda_fill (CUDA events) */
+float stb_cuda_last_fill_ms(const stb_dev_t *d);
+
+/*
+ * Copy rows [row0, row0+nrows) (0-based row index = n-1) of one table to host memory as
+ * doubles (float tables are widened on the host side of the copy).  dst holds nrows*ld doubles.
+ */
+int stb_cuda_read_rows(stb_dev_t *d, int which, unsigned row0, unsigned nrows, double *dst);
+
+/*
+ * out[i] = look-up of (n[i], m[i]) in table `which`, evaluated on the device with the scalar
+ * API's in-range conventions (S: n==m -> 0, m==0 or n<m -> -inf; V: m<2 or n<m -> 0); pairs
+ * beyond usedN/usedM answer -inf / 0 (the C layer grows the table first when it may).
+ * n, m, out are HOST pointers when on_device==0 (staged) or DEVICE pointers otherwise.
+ */
+int stb_cuda_gather(stb_dev_t *d, int which, unsigned usedN, unsigned usedM, const uint32_t *n,
+                    const uint32_t *m, double *out, size_t count, int on_device);
+
+/* raw device pointer of a table (for the batched samplers and for tests) */
+void *stb_cuda_table_ptr(stb_dev_t *d, int which);
+
+/* pinned host memory for mirrors */
+void *stb_cuda_host_alloc(size_t bytes);
+void stb_cuda_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,45 @@
+#!/bin/bash
+# Builds the UNMODIFIED reference library (wbuntine/libstb, /root/reference/lib/*.c) into
+# oracle/_ref/ as shared objects, compiling the sources where they lie.  Nothing from the
+# reference is copied into the repository: oracle/_ref/ is git-ignored and holds only .so files.
+#
+#   oracle/_ref/libstb_ref.so        default configuration of lib/Makefile:7 (-O5 -DNDEBUG -DH_THREADS;
+#                                    PSAMPLE_ARS + LS_NOPOLYGAMMA defined => ARS samplers, digammaRN)
+#   oracle/_ref/libstb_ref_slice.so  slice-sampler configuration: PSAMPLE_ARS and
+#                                    LS_NOPOLYGAMMA undefined and polygamma.c added, so that
+#                                    samplea/sampleb run SliceSimple and bmax/digammaInv exist.
+#
+# The two switches are "#define"s inside lib/psample.h:37 and lib/digamma.h:25, not -D flags, so the
+# slice build compiles through a throw-away directory under /tmp that holds symlinks to the sources
+# and sed-filtered copies of those two headers; the directory is removed afterwards.
+#
+# This is TEST INFRASTRUCTURE (the checker / the CPU baseline), never part of the product path.
+set -euo pipefail
+REF=${STB_REFERENCE_DIR:-/root/reference}
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+OUT="$HERE/_ref"
+CC=${CC:-gcc}
+if [ ! -d "$REF/lib" ]; then
+  echo "build_ref.sh: $REF/lib not present (GPU box?) - keeping prebuilt files in $OUT" >&2
+  exit 0
+fi
+mkdir -p "$OUT"
+CFLAGS="-O3 -DNDEBUG -DH_THREADS -fPIC -w"
+SRC="stable digamma arms sapprox sslice sampleb samplea yaps lgamma sympoly digammainv gslrandist"
+
+# --- default (ARS) configuration, sources compiled in place ---
+files=""
+for s in $SRC; do files="$files $REF/lib/$s.c"; done
+$CC $CFLAGS -shared -o "$OUT/libstb_ref.so" $files -lm -lpthread
+
+# --- slice configuration ---
+TMP=$(mktemp -d /tmp/stbref.XXXXXX)
+trap 'rm -rf "$TMP"' EXIT
+for f in "$REF"/lib/*.c "$REF"/lib/*.h; do ln -s "$f" "$TMP/$(basename "$f")"; done
+rm "$TMP/psample.h" "$TMP/digamma.h"
+sed 's|^#define PSAMPLE_ARS|// &|' "$REF/lib/psample.h" > "$TMP/psample.h"
+sed 's|^#define LS_NOPOLYGAMMA|// &|' "$REF/lib/digamma.h" > "$TMP/digamma.h"
+files=""
+for s in $SRC polygamma; do files="$files $TMP/$s.c"; done
+$CC $CFLAGS -shared -o "$OUT/libstb_ref_slice.so" $files -lm -lpthread
+echo "built $OUT/libstb_ref.so $OUT/libstb_ref_slice.so"

@@ -1,0 +1,52 @@
+/*
+ * stirling_oracle.h -- CPU restatement of the reference's table algorithm.
+ * TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline leg.  The product (libstb_b200) never links or calls this.
+ */
+#ifndef STIRLING_ORACLE_H
+#define STIRLING_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* flag bits, same values as lib/stable.h:38-44 */
+#define ORC_STABLE 1
+#define ORC_UVTABLE 2
+#define ORC_FLOAT 4
+#define ORC_QUITONBOUND 16
+#define ORC_ASYMPT 64
+
+/* Dense tables: cell (n,m) at [(n-1)*ld + (m-1)], valid for 1<=m<=min(n,M). */
+void orc_fill_S1(unsigned N, double a, double *S1);
+void orc_fill_S(unsigned N, unsigned M, double a, double *S, size_t ld);
+void orc_fill_V(unsigned N, unsigned M, double a, double *V, size_t ld);
+
+/* a fixed-extent table object with the reference's look-up conventions (no growth) */
+typedef struct orc_table {
+  unsigned N, M, maxN, maxM;
+  double a, lga;
+  uint32_t flags;
+  size_t ld;
+  double *S, *V, *S1;
+} orc_table;
+
+orc_table *orc_make(unsigned N, unsigned M, unsigned maxN, unsigned maxM, double a, uint32_t flags);
+void orc_free(orc_table *t);
+double orc_S(const orc_table *t, unsigned n, unsigned m);
+double orc_S1(const orc_table *t, unsigned n);
+double orc_V(const orc_table *t, unsigned n, unsigned m);
+double orc_U(const orc_table *t, unsigned n, unsigned m);
+double orc_UV(const orc_table *t, unsigned n, unsigned m);
+double orc_asympt(double a, unsigned n, unsigned m);
+double orc_V_asympt(double a, unsigned n, unsigned m);
+
+/* number of stored cells with m>=2, SURVEY.md section 8 */
+uint64_t orc_cells_S(uint64_t N, uint64_t M);
+uint64_t orc_cells_V(uint64_t N, uint64_t M);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,66 @@
+"""BASELINE configs at full size, checked through size-independent properties and the spot
+values the reference produced for them.  The CPU oracle needs ~150 s and 31 GB
+for config 2, so the full-size check uses: golden spot cells; the column-prefix property (a
+table's first M' columns do not depend on M, so they must equal the oracle run at M'=256);
+identities S^n_n=1, S^n_{n-1}=n(n-1)(1-a)/2, S(n,1)=lgamma(n-a)-lgamma(1-a), U=S(n+1)-S(n)."""
+import math
+
+import numpy as np
+import pytest
+
+import libstb_b200 as stb
+from tests import harness
+
+pytestmark = pytest.mark.gpu
+
+
+def test_config2_large_single_table():
+    N, M, a = 200000, 20000, 0.7
+    t = stb.Table(N, M, N, M, a, stb.S_STABLE)
+    # spot values from the reference build
+    assert harness.close(t.S(200000, 20000), 2070256.428328451).all()
+    assert harness.close(t.S(200000, 2), 2241200.0617941185).all()
+    assert harness.close(t.S(200000, 10000), 2162666.1833218271).all()
+    # column prefix vs the oracle at M'=256
+    Mp = 256
+    S, _ = harness.oracle_tables(N, Mp, a, want_V=False)
+    rng = np.random.default_rng(11)
+    rows = np.unique(np.concatenate([rng.integers(2, N + 1, size=400), [N, N - 1, 257, 256, 255]]))
+    for n in rows:
+        g = t.rows(0, int(n), 1)[0, :Mp]
+        top = min(int(n), Mp)
+        assert harness.close(g[:top], S[n - 1, :top]).all(), n
+    # identities on cells the prefix does not reach
+    nn = rng.integers(3, N + 1, size=200000).astype(np.uint32)
+    mm = np.minimum(rng.integers(2, M + 1, size=200000), nn - 1).astype(np.uint32)
+    s0 = t.S_batch(nn, mm)
+    assert np.isfinite(s0).all()
+    # monotone in n for fixed m: S^{n+1}_m > S^n_m  (U > 1 for n >= 2)
+    k = nn < N
+    s1 = t.S_batch(nn[k] + 1, mm[k])
+    assert (s1 > s0[k]).all()
+    for n in (5, 100, 19999, 20000):
+        assert t.S(n, n) == 0.0
+        assert harness.close(t.S(n, n - 1), math.log(n * (n - 1) * (1 - a) / 2)).all()
+    for n in (2, 1000, 200000):
+        assert harness.close(t.S(n, 1), math.lgamma(n - a) - math.lgamma(1 - a)).all()
+    t.free()
+
+
+def test_config3_shape_with_V():
+    N, M, a = 50000, 5000, 0.7
+    t = stb.Table(N, M, N, M, a, stb.S_STABLE | stb.S_UVTABLE)
+    assert harness.close(t.S(50000, 5000), 455174.29062118637).all()
+    rng = np.random.default_rng(5)
+    nn = rng.integers(3, N, size=50000).astype(np.uint32)
+    mm = np.minimum(rng.integers(2, M + 1, size=50000), nn - 1).astype(np.uint32)
+    s0, s1 = t.S_batch(nn, mm), t.S_batch(nn + 1, mm)
+    v = t.V_batch(nn, mm)
+    # U^n_m = n - m a + 1/V^n_m = S^{n+1}_m / S^n_m    (lib/stable.c:875-883)
+    u = nn - mm * a + 1.0 / v
+    assert np.allclose(np.log(u), s1 - s0, rtol=0, atol=2e-9)
+    # V^n_m = S^n_m / S^n_{m-1}
+    sm = t.S_batch(nn, mm - 1)
+    k = mm >= 3
+    assert np.allclose(np.log(v[k]), (s0 - sm)[k], rtol=0, atol=2e-9)
+    t.free()
