@@ -38,10 +38,11 @@
 namespace stb {
 
 constexpr int LIN_B = 8;          // steps per batch; a lane renormalises once per batch
-constexpr int LIN_RB = 128;       // boundary ring entries in shared memory (power of two)
-constexpr int LIN_RBG = 1024;     // boundary ring entries in global memory per CTA boundary
+constexpr int LIN_RBI = 64;       // boundary ring entries between two strips of one CTA (power of two)
+constexpr int LIN_RBX = 256;      // boundary ring entries at a CTA edge (fed/drained through L2)
+constexpr int LIN_RBG = 2048;     // boundary ring entries in global memory per CTA boundary
 constexpr int LIN_CONS = 2;       // consumer warps per warp-strip
-constexpr int LIN_CHUNK = 32;     // rows moved per loader/flusher copy
+constexpr int LIN_CHUNK = 32;     // least rows a loader/flusher moves per round trip
 constexpr int LIN_LOGTAB = 257;   // log table entries
 constexpr long long LIN_WATCHDOG = 6000000000LL;  // cycles a wait may last before the fill aborts
 
@@ -81,11 +82,12 @@ struct LinParams {
 __device__ __forceinline__ int ld_vol(const int *p) { return *(const volatile int *)p; }
 __device__ __forceinline__ void st_vol(int *p, int v) { *(volatile int *)p = v; }
 
-__device__ __forceinline__ int ld_acquire_gpu(const int *p) {
+__device__ __forceinline__ int ld_relaxed_gpu(const int *p) {
   int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void st_release_gpu(int *p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -101,31 +103,44 @@ __device__ __forceinline__ double shfl_up_d(double v) {
 }
 
 /*
- * Spin until *ctr >= need.  Returns false if the fill was aborted (watchdog or another role's
- * failure); every role then drains out of the kernel so that a protocol bug can never hang
- * the GPU.
+ * Warp-collective wait until *ctr >= need (all 32 lanes call it with the same arguments; the
+ * counter load is one broadcast access, so every lane sees the same value and the loop stays
+ * converged).  Returns false if the fill was aborted (watchdog or another role's failure);
+ * every role then drains out of the kernel, so a protocol bug can never hang the GPU.
+ *
+ * Ordering inside a CTA: the counters and the data they guard live in shared memory, whose
+ * accesses the SM performs in issue order -- ptxas itself lowers ld.acquire.cta.shared to a
+ * plain LDS and mbarrier.arrive.release to a bare SYNCS -- so the shared-memory protocol uses
+ * volatile accesses plus compiler barriers and no MEMBAR (a MEMBAR.SC.CTA per hand-off costs
+ * more than the eight recurrence steps it guards).  The global-memory hand-off between CTAs
+ * uses real release/acquire.
  */
 template <bool GLOBAL, int SLEEP>
 __device__ __forceinline__ bool wait_ge(const int *ctr, int need, int *abort_flag, int &cached) {
   if (cached >= need) return true;
-  long long t0 = clock64();
-  unsigned spins = 0;
-  for (;;) {
-    int v = GLOBAL ? ld_acquire_gpu(ctr) : ld_vol(ctr);
-    if (v >= need) {
-      cached = v;
-      if (!GLOBAL) __threadfence_block();
-      return true;
-    }
-    if (SLEEP) __nanosleep(SLEEP);
-    if ((++spins & 1023u) == 0) {
-      if (ld_vol(abort_flag)) return false;
-      if (clock64() - t0 > LIN_WATCHDOG) {
-        atomicExch(abort_flag, 1);
-        return false;
+  // global counters are polled relaxed; one acquire fence follows the successful read
+  int v = GLOBAL ? ld_relaxed_gpu(ctr) : ld_vol(ctr);
+  if (v < need) {
+    const long long t0 = clock64();
+    unsigned spins = 0;
+    do {
+      if (SLEEP) __nanosleep(SLEEP);
+      v = GLOBAL ? ld_relaxed_gpu(ctr) : ld_vol(ctr);
+      if ((++spins & 1023u) == 0) {
+        const int bad = ld_vol(abort_flag) || (clock64() - t0 > LIN_WATCHDOG);
+        if (__any_sync(0xffffffffu, bad)) {
+          if ((threadIdx.x & 31) == 0) atomicExch(abort_flag, 1);
+          return false;
+        }
       }
-    }
+    } while (v < need);
   }
+  cached = v;
+  if (GLOBAL)
+    fence_acq_rel_gpu();
+  else
+    asm volatile("" ::: "memory");
+  return true;
 }
 
 /*
@@ -167,10 +182,11 @@ struct LinSmem {
   static constexpr size_t yring_bytes = HAS_V ? (size_t)RS * 32 * 8 : 0;
   static constexpr size_t ering_bytes = (size_t)NJ * 32 * 8;
   static constexpr size_t strip_bytes = xring_bytes + yring_bytes + ering_bytes;
-  static constexpr size_t ring_bytes = (size_t)LIN_RB * sizeof(BndEntry);
-  // layout: logtab | (G+1) boundary rings | G strips | control words
+  static constexpr size_t ringi_bytes = (size_t)LIN_RBI * sizeof(BndEntry);
+  static constexpr size_t ringx_bytes = (size_t)LIN_RBX * sizeof(BndEntry);
+  // layout: logtab | 2 edge rings | (G-1) interior rings | G strips | control words
   __host__ __device__ static size_t total(int G) {
-    return (size_t)LIN_LOGTAB * sizeof(LogTabEntry) + 16 + (size_t)(G + 1) * ring_bytes +
+    return (size_t)LIN_LOGTAB * sizeof(LogTabEntry) + 16 + 2 * ringx_bytes + (size_t)(G - 1) * ringi_bytes +
            (size_t)G * strip_bytes + (size_t)(G + 1) * sizeof(RingCtl) +
            (size_t)G * (1 + LIN_CONS) * sizeof(int) + 64;
   }
@@ -182,8 +198,8 @@ struct LinSmem {
 template <int K, bool HAS_V, int RS, bool EDGE>
 __device__ __forceinline__ void producer_batch(
     double (&x)[K], double &yin, int &elow, const double (&ma)[K], double &nm1, int n_lane, int rs,
-    int N, int lane, bool left_seed, bool has_right, const BndEntry *ring_in, BndEntry *ring_out,
-    double *xring, double *yring) {
+    int N, int lane, bool left_seed, bool has_right, const BndEntry *ring_in, int mask_in,
+    BndEntry *ring_out, int mask_out, double *xring, double *yring) {
   constexpr int W = 32 * K;
 #pragma unroll
   for (int i = 0; i < LIN_B; i++) {
@@ -198,7 +214,7 @@ __device__ __forceinline__ void producer_batch(
         sE = elow;
       } else {
         int rn = n < N ? n : N;
-        const BndEntry e = ring_in[rn & (LIN_RB - 1)];
+        const BndEntry e = ring_in[rn & mask_in];
         s = e.x;
         sE = e.elow;
       }
@@ -232,7 +248,7 @@ __device__ __forceinline__ void producer_batch(
         e.x = x[K - 1];
         e.elow = elow;
         e.pad = 0;
-        ring_out[n & (LIN_RB - 1)] = e;
+        ring_out[n & mask_out] = e;
       }
     }
   }
@@ -240,8 +256,8 @@ __device__ __forceinline__ void producer_batch(
 
 template <int K, bool HAS_V, int RS>
 __device__ void producer_warp(const LinParams &P, int ws, int lane, bool left_seed, bool has_right,
-                              const BndEntry *ring_in, RingCtl *ctl_in, BndEntry *ring_out,
-                              RingCtl *ctl_out, double *xring, double *yring, double *ering,
+                              const BndEntry *ring_in, int mask_in, RingCtl *ctl_in, BndEntry *ring_out,
+                              int mask_out, RingCtl *ctl_out, double *xring, double *yring, double *ering,
                               int *prod_done, const int *cfin) {
   constexpr int W = 32 * K;
   constexpr int NJ = LinSmem<K, HAS_V, RS>::NJ;
@@ -270,7 +286,7 @@ __device__ void producer_warp(const LinParams &P, int ws, int lane, bool left_se
     // initial left value: the boundary entry of row rs
     if (!wait_ge<false, 0>(&ctl_in->written, rs, P.abort_flag, c_in)) return;
     if (lane == 0) {
-      const BndEntry e = ring_in[rs & (LIN_RB - 1)];
+      const BndEntry e = ring_in[rs & mask_in];
       yin = e.x * pow2i(e.elow - elow);
     }
   }
@@ -282,8 +298,8 @@ __device__ void producer_warp(const LinParams &P, int ws, int lane, bool left_se
       e.x = 0.0;
       e.elow = 0;
       e.pad = 0;
-      ring_out[rs & (LIN_RB - 1)] = e;
-      __threadfence_block();
+      ring_out[rs & mask_out] = e;
+      asm volatile("" ::: "memory");
       st_vol(&ctl_out->written, rs);
     }
     __syncwarp();
@@ -299,25 +315,33 @@ __device__ void producer_warp(const LinParams &P, int ws, int lane, bool left_se
     }
     if (has_right) {
       // lane 31 will write rows up to top0-31; slot reuse needs row-RB taken
-      int need = top0 - 31 - LIN_RB;
+      int need = top0 - 31 - (mask_out + 1);
       if (!wait_ge<false, 0>(&ctl_out->taken, need, P.abort_flag, c_out)) return;
     }
     {
-      // xring slot reuse: rows <= top0-RS must have been consumed
-      int need = top0 - RS;
-      while (c_cons < need) {
-        int mn = ld_vol(cfin);
+      // xring slot reuse: rows <= top0-RS must have been consumed by every consumer warp
+      const int need = top0 - RS;
+      if (c_cons < need) {
+        const long long tw = clock64();
+        unsigned spins = 0;
+        for (;;) {
+          int mn = ld_vol(cfin);
 #pragma unroll
-        for (int c = 1; c < LIN_CONS; c++) {
-          int v = ld_vol(cfin + c);
-          mn = v < mn ? v : mn;
+          for (int c = 1; c < LIN_CONS; c++) {
+            int v = ld_vol(cfin + c);
+            mn = v < mn ? v : mn;
+          }
+          c_cons = (bfirst + mn + LIN_CONS) * LIN_B - 1;
+          if (c_cons >= need) break;
+          if ((++spins & 1023u) == 0) {
+            const int bad = ld_vol(P.abort_flag) || (clock64() - tw > LIN_WATCHDOG);
+            if (__any_sync(0xffffffffu, bad)) {
+              if (lane == 0) atomicExch(P.abort_flag, 1);
+              return;
+            }
+          }
         }
-        c_cons = (bfirst + mn + LIN_CONS) * LIN_B - 1;
-        if (c_cons >= need) {
-          __threadfence_block();
-          break;
-        }
-        if (ld_vol(P.abort_flag)) return;
+        asm volatile("" ::: "memory");
       }
     }
     // ---- renormalise (uniform step) ----
@@ -338,14 +362,14 @@ __device__ void producer_warp(const LinParams &P, int ws, int lane, bool left_se
     const bool edge = (t0 < 32) || (top0 > N);
     if (edge)
       producer_batch<K, HAS_V, RS, true>(x, yin, elow, ma, nm1, n_lane, rs, N, lane, left_seed, has_right,
-                                         ring_in, ring_out, xring, yring);
+                                         ring_in, mask_in, ring_out, mask_out, xring, yring);
     else
       producer_batch<K, HAS_V, RS, false>(x, yin, elow, ma, nm1, n_lane, rs, N, lane, left_seed,
-                                          has_right, ring_in, ring_out, xring, yring);
+                                          has_right, ring_in, mask_in, ring_out, mask_out, xring, yring);
     // ---- publish ----
     __syncwarp();
+    asm volatile("" ::: "memory");
     if (lane == 31) {
-      __threadfence_block();
       int done = top0 - 31;
       if (done > N) done = N;
       if (done > rs) {
@@ -363,12 +387,25 @@ __device__ void producer_warp(const LinParams &P, int ws, int lane, bool left_se
 // ---------------------------------------------------------------------------------------------
 // consumer: log / divide / store, LIN_CONS warps per warp-strip
 // ---------------------------------------------------------------------------------------------
+/* x / d for normal positive operands: MUFU seed + two Newton steps + one correction, no branch */
+__device__ __forceinline__ double div_pos(double x, double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  double q = x * r;
+  return fma(fma(-d, q, x), r, q);
+}
+
 template <int K, bool HAS_S, bool HAS_V, int RS, typename OutT>
 __device__ void consumer_warp(const LinParams &P, int ws, int cidx, int lane, const double *xring,
                               const double *yring, const double *ering, const int *prod_done, int *cfin,
                               const LogTabEntry *logtab) {
   constexpr int W = 32 * K;
   constexpr int NJ = LinSmem<K, HAS_V, RS>::NJ;
+  constexpr double EBIAS = 4503601774854144.0;  // 2^52 + 2^31
   const int N = P.N, M = P.M;
   const int m_first = ws * W + 1;
   const int rs = m_first - 1;
@@ -381,89 +418,138 @@ __device__ void consumer_warp(const LinParams &P, int ws, int cidx, int lane, co
     const int nb = (bfirst + bb) << 3;
     int top = nb + LIN_B - 1;
     if (top > N) top = N;
-    if (!wait_ge<false, 64>(prod_done, top, P.abort_flag, c_done)) return;
+    if (!wait_ge<false, 0>(prod_done, top, P.abort_flag, c_done)) return;
+    const int slot0 = nb & (RS - 1);  // the block's eight ring rows are contiguous
 #pragma unroll
     for (int kk = 0; kk < K; kk++) {
       const int col = lane + 32 * kk;
       const int m = m_first + col;
       const int pl = col / K;
       const int kq = col % K;
-      if (m > M) continue;
+      const bool full = (nb > rs) && (nb + LIN_B - 1 <= N) && (m <= nb) && (m <= M);
+      if (full) {
+        // ---- steady state: eight rows, no predicates, loads first so they overlap ----
+        double xv[LIN_B];
 #pragma unroll
-      for (int i = 0; i < LIN_B; i++) {
-        const int n = nb + i;
-        if (n > N || n <= rs || m > n) continue;
-        const int slot = n & (RS - 1);
-        const double xv = xring[(size_t)slot * W + col];
-        const size_t off = (size_t)(n - 1) * P.ld + (size_t)(m - 1);
+        for (int i = 0; i < LIN_B; i++) xv[i] = xring[(size_t)(slot0 + i) * W + col];
+        OutT *pS = HAS_S ? tabS + (size_t)(nb - 1) * P.ld + (size_t)(m - 1) : nullptr;
+        OutT *pV = HAS_V ? tabV + (size_t)(nb - 1) * P.ld + (size_t)(m - 1) : nullptr;
         if (HAS_S) {
-          const int j = (n - rs - 1 + pl) >> 3;
-          const double Eoff = ering[(j & (NJ - 1)) * 32 + pl] - 4503601774854144.0;
-          const double v = log_scaled(xv, Eoff, logtab);
-          st_out(tabS + off, v);
-          if (m == 1) P.s1[n - 1] = v;
+          // lane pl computed row n at step n-rs-1+pl; its exponent changes every eighth step
+          const int toff = nb - rs - 1 + pl;
+          const int j0 = toff >> 3, thr = 8 - (toff & 7);
+          const double Ea = ering[(j0 & (NJ - 1)) * 32 + pl] - EBIAS;
+          const double Eb = ering[((j0 + 1) & (NJ - 1)) * 32 + pl] - EBIAS;
+          double v[LIN_B];
+#pragma unroll
+          for (int i = 0; i < LIN_B; i++) v[i] = log_scaled(xv[i], (i >= thr) ? Eb : Ea, logtab);
+#pragma unroll
+          for (int i = 0; i < LIN_B; i++) st_out(pS + (size_t)i * P.ld, v[i]);
+          if (m == 1) {
+#pragma unroll
+            for (int i = 0; i < LIN_B; i++) P.s1[nb - 1 + i] = v[i];
+          }
         }
         if (HAS_V && m >= 2) {
-          const double den = (kq == 0) ? yring[slot * 32 + pl] : xring[(size_t)slot * W + col - 1];
-          st_out(tabV + off, xv / den);
+          double den[LIN_B];
+#pragma unroll
+          for (int i = 0; i < LIN_B; i++)
+            den[i] = (kq == 0) ? yring[(slot0 + i) * 32 + pl] : xring[(size_t)(slot0 + i) * W + col - 1];
+#pragma unroll
+          for (int i = 0; i < LIN_B; i++) st_out(pV + (size_t)i * P.ld, div_pos(xv[i], den[i]));
+        }
+      } else if (m <= M) {
+        // ---- edges: first rows of the strip (triangle), last partial block ----
+        for (int i = 0; i < LIN_B; i++) {
+          const int n = nb + i;
+          if (n > N || n <= rs || m > n) continue;
+          const int slot = n & (RS - 1);
+          const double xv = xring[(size_t)slot * W + col];
+          const size_t off = (size_t)(n - 1) * P.ld + (size_t)(m - 1);
+          if (HAS_S) {
+            const int j = (n - rs - 1 + pl) >> 3;
+            const double v = log_scaled(xv, ering[(j & (NJ - 1)) * 32 + pl] - EBIAS, logtab);
+            st_out(tabS + off, v);
+            if (m == 1) P.s1[n - 1] = v;
+          }
+          if (HAS_V && m >= 2) {
+            const double den = (kq == 0) ? yring[slot * 32 + pl] : xring[(size_t)slot * W + col - 1];
+            st_out(tabV + off, div_pos(xv, den));
+          }
         }
       }
     }
     __syncwarp();
-    if (lane == 0) {
-      __threadfence_block();
-      st_vol(cfin + cidx, bb);
-    }
+    asm volatile("" ::: "memory");
+    if (lane == 0) st_vol(cfin + cidx, bb);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// loader / flusher: inter-CTA hand-off of the boundary column through an L2-resident ring
+// loader / flusher: inter-CTA hand-off of the boundary column through an L2-resident ring.
+// Both move EVERYTHING that is available per round trip, so a helper that falls behind
+// amortises its global-memory latency over more rows and catches up by itself.
 // ---------------------------------------------------------------------------------------------
 __device__ void loader_warp(const LinParams &P, int cta, int rs0, int lane, BndEntry *ring0, RingCtl *ctl0) {
-  // reads the ring written by CTA cta-1; feeds shared-memory ring 0
+  // reads the ring written by CTA cta-1; feeds the CTA's input edge ring
   const BndEntry *g = P.gring + (size_t)(cta - 1) * LIN_RBG;
   const int last = P.N;  // rows rs0..N are published by the left CTA
-  int c_w = 0, c_t = rs0 - 1;
+  int c_w = 0, c_t = rs0 - 1, pub = rs0 - 1;
   if (lane == 0) st_release_gpu(P.gtaken + (cta - 1), rs0 - 1);
-  for (int next = rs0; next <= last; next += LIN_CHUNK) {
+  for (int next = rs0; next <= last;) {
     int top = next + LIN_CHUNK - 1;
     if (top > last) top = last;
-    if (!wait_ge<true, 32>(P.gwritten + (cta - 1), top, P.abort_flag, c_w)) return;
-    if (!wait_ge<false, 32>(&ctl0->taken, top - LIN_RB, P.abort_flag, c_t)) return;
-    const int row = next + lane;
-    if (row <= top) {
-      BndEntry e = g[row & (LIN_RBG - 1)];
-      ring0[row & (LIN_RB - 1)] = e;
+    if (!wait_ge<true, 0>(P.gwritten + (cta - 1), top, P.abort_flag, c_w)) return;
+    if (!wait_ge<false, 0>(&ctl0->taken, top - LIN_RBX, P.abort_flag, c_t)) return;
+    int hi = c_w < last ? c_w : last;
+    if (hi > c_t + LIN_RBX) hi = c_t + LIN_RBX;
+    for (int base = next; base <= hi; base += 128) {
+      BndEntry e[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int row = base + 32 * u + lane;
+        if (row <= hi) e[u] = g[row & (LIN_RBG - 1)];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int row = base + 32 * u + lane;
+        if (row <= hi) ring0[row & (LIN_RBX - 1)] = e[u];
+      }
     }
     __syncwarp();
+    asm volatile("" ::: "memory");
     if (lane == 0) {
-      __threadfence_block();
-      st_vol(&ctl0->written, top);
-      st_release_gpu(P.gtaken + (cta - 1), top);
+      st_vol(&ctl0->written, hi);
+      if (hi - pub >= LIN_RBG / 4 || hi == last) {
+        st_release_gpu(P.gtaken + (cta - 1), hi);
+        pub = hi;
+      }
     }
+    pub = __shfl_sync(0xffffffffu, pub, 0);
+    next = hi + 1;
   }
 }
 
 __device__ void flusher_warp(const LinParams &P, int cta, int rsl, int lane, const BndEntry *ringG,
                              RingCtl *ctlG) {
-  // drains the last strip's output ring into the global ring read by CTA cta+1
+  // drains the last strip's output edge ring into the global ring read by CTA cta+1
   BndEntry *g = P.gring + (size_t)cta * LIN_RBG;
   const int last = P.N;
   int c_w = rsl - 1, c_t = 0;
-  for (int next = rsl; next <= last; next += LIN_CHUNK) {
+  for (int next = rsl; next <= last;) {
     int top = next + LIN_CHUNK - 1;
     if (top > last) top = last;
-    if (!wait_ge<false, 32>(&ctlG->written, top, P.abort_flag, c_w)) return;
-    if (!wait_ge<true, 32>(P.gtaken + cta, top - LIN_RBG, P.abort_flag, c_t)) return;
-    const int row = next + lane;
-    if (row <= top) g[row & (LIN_RBG - 1)] = ringG[row & (LIN_RB - 1)];
+    if (!wait_ge<false, 0>(&ctlG->written, top, P.abort_flag, c_w)) return;
+    if (!wait_ge<true, 0>(P.gtaken + cta, top - LIN_RBG, P.abort_flag, c_t)) return;
+    int hi = c_w < last ? c_w : last;
+    if (hi > c_t + LIN_RBG) hi = c_t + LIN_RBG;
+    for (int row = next + lane; row <= hi; row += 32) g[row & (LIN_RBG - 1)] = ringG[row & (LIN_RBX - 1)];
     __syncwarp();
     if (lane == 0) {
-      __threadfence();
-      st_release_gpu(P.gwritten + cta, top);
-      st_vol(&ctlG->taken, top);
+      st_release_gpu(P.gwritten + cta, hi);  // release orders the whole warp's stores (syncwarp above)
+      st_vol(&ctlG->taken, hi);
     }
+    next = hi + 1;
   }
 }
 
@@ -481,8 +567,12 @@ __global__ void __launch_bounds__(1024, 1) fill_linear_kernel(const LinParams P)
 
   LogTabEntry *logtab = reinterpret_cast<LogTabEntry *>(smem);
   unsigned char *p = smem + (((size_t)LIN_LOGTAB * sizeof(LogTabEntry) + 15) & ~(size_t)15);
-  BndEntry *rings = reinterpret_cast<BndEntry *>(p);
-  p += (size_t)(G + 1) * SM::ring_bytes;
+  BndEntry *ring_in_edge = reinterpret_cast<BndEntry *>(p);
+  p += SM::ringx_bytes;
+  BndEntry *ring_out_edge = reinterpret_cast<BndEntry *>(p);
+  p += SM::ringx_bytes;
+  BndEntry *rings_int = reinterpret_cast<BndEntry *>(p);  // ring g (1<=g<G) at rings_int + (g-1)*RBI
+  p += (size_t)(G - 1) * SM::ringi_bytes;
   unsigned char *strips = p;
   p += (size_t)G * SM::strip_bytes;
   RingCtl *ctl = reinterpret_cast<RingCtl *>(p);
@@ -523,9 +613,14 @@ __global__ void __launch_bounds__(1024, 1) fill_linear_kernel(const LinParams P)
       double *ering = reinterpret_cast<double *>(sb + SM::xring_bytes + SM::yring_bytes);
       const bool left_seed = (ws == 0);
       const bool has_right = !(last_cta && g == nloc - 1);
-      producer_warp<K, HAS_V, RS>(P, ws, lane, left_seed, has_right, rings + (size_t)g * LIN_RB, ctl + g,
-                                  rings + (size_t)(g + 1) * LIN_RB, ctl + g + 1, xring, yring, ering,
-                                  prod_done + g, cfin + g * LIN_CONS);
+      // ring g feeds strip g, ring g+1 takes its last column; the CTA's first and last rings are
+      // the large edge rings, the ones in between are small
+      const BndEntry *rin = (g == 0) ? ring_in_edge : rings_int + (size_t)(g - 1) * LIN_RBI;
+      const int min_ = (g == 0) ? LIN_RBX - 1 : LIN_RBI - 1;
+      BndEntry *rout = (g == nloc - 1) ? ring_out_edge : rings_int + (size_t)g * LIN_RBI;
+      const int mout = (g == nloc - 1) ? LIN_RBX - 1 : LIN_RBI - 1;
+      producer_warp<K, HAS_V, RS>(P, ws, lane, left_seed, has_right, rin, min_, ctl + g, rout, mout,
+                                  ctl + g + 1, xring, yring, ering, prod_done + g, cfin + g * LIN_CONS);
     }
   } else if (warp < G + G * LIN_CONS) {
     const int g = (warp - G) / LIN_CONS, c = (warp - G) % LIN_CONS;
@@ -538,9 +633,9 @@ __global__ void __launch_bounds__(1024, 1) fill_linear_kernel(const LinParams P)
                                                cfin + g * LIN_CONS, logtab);
     }
   } else if (warp == G + G * LIN_CONS) {
-    if (cta > 0) loader_warp(P, cta, ws0 * W, lane, rings, ctl);
+    if (cta > 0) loader_warp(P, cta, ws0 * W, lane, ring_in_edge, ctl);
   } else {
-    if (!last_cta) flusher_warp(P, cta, (ws0 + nloc - 1) * W, lane, rings + (size_t)nloc * LIN_RB, ctl + nloc);
+    if (!last_cta) flusher_warp(P, cta, (ws0 + nloc - 1) * W, lane, ring_out_edge, ctl + nloc);
   }
 }
 
