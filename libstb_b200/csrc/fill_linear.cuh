@@ -35,6 +35,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include "fill_common.cuh"
+
 namespace stb {
 
 constexpr int LIN_B = 8;          // steps per batch; a lane renormalises once per batch
@@ -43,18 +45,13 @@ constexpr int LIN_RBX = 256;      // boundary ring entries at a CTA edge (fed/dr
 constexpr int LIN_RBG = 2048;     // boundary ring entries in global memory per CTA boundary
 constexpr int LIN_CONS = 2;       // consumer warps per warp-strip
 constexpr int LIN_CHUNK = 32;     // least rows a loader/flusher moves per round trip
-constexpr int LIN_LOGTAB = 257;   // log table entries
-constexpr long long LIN_WATCHDOG = 6000000000LL;  // cycles a wait may last before the fill aborts
+constexpr int LIN_LOGTAB = LOGTAB_N;
+constexpr long long LIN_WATCHDOG = FILL_WATCHDOG;
 
 struct __align__(16) BndEntry {
   double x;  // value of the strip's last column at this row, in units of 2^E
   int elow;  // low 32 bits of that lane's E
   int pad;
-};
-
-struct __align__(16) LogTabEntry {
-  double inv_c;  // 1/c_i rounded, c_i = 1 + i/256
-  double log_c;  // -log(inv_c) in double
 };
 
 struct RingCtl {
@@ -75,32 +72,6 @@ struct LinParams {
   int *abort_flag;
   const LogTabEntry *logtab;
 };
-
-// ---------------------------------------------------------------------------------------------
-// small device helpers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int ld_vol(const int *p) { return *(const volatile int *)p; }
-__device__ __forceinline__ void st_vol(int *p, int v) { *(volatile int *)p = v; }
-
-__device__ __forceinline__ int ld_relaxed_gpu(const int *p) {
-  int v;
-  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
-__device__ __forceinline__ void st_release_gpu(int *p, int v) {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-__device__ __forceinline__ double pow2i(int e) {  // 2^e, |e| <= 1022
-  return __hiloint2double((e + 1023) << 20, 0);
-}
-
-__device__ __forceinline__ double shfl_up_d(double v) {
-  int lo = __shfl_up_sync(0xffffffffu, __double2loint(v), 1);
-  int hi = __shfl_up_sync(0xffffffffu, __double2hiint(v), 1);
-  return __hiloint2double(hi, lo);
-}
 
 /*
  * Warp-collective wait until *ctr >= need (all 32 lanes call it with the same arguments; the
@@ -141,34 +112,6 @@ __device__ __forceinline__ bool wait_ge(const int *ctr, int need, int *abort_fla
   else
     asm volatile("" ::: "memory");
   return true;
-}
-
-/*
- * log(x * 2^E) for x > 0 finite normal; Eoff = (double)E - (2^52 + 2^31).
- * Table-driven: x = 2^k * mant, mant in [1,2); c = 1 + i/256 nearest to mant; r = mant/c - 1
- * (|r| <= 2^-9, one FMA); log(mant) = log1p(r) + log(c); result = (E+k) ln2 + log(c) + log1p(r)
- * with E+k formed exactly.  mant == 1 gives exactly (E+k) ln2, so S^n_n comes out as +0.0.
- */
-__device__ __forceinline__ double log_scaled(double x, double Eoff, const LogTabEntry *tab) {
-  const int hi = __double2hiint(x), lo = __double2loint(x);
-  const int k = (hi >> 20) - 1023;
-  const int frac = hi & 0xFFFFF;
-  const int idx = (frac + 0x800) >> 12;
-  const double mant = __hiloint2double(frac | 0x3FF00000, lo);
-  const double2 tb = *reinterpret_cast<const double2 *>(tab + idx);
-  const double r = fma(mant, tb.x, -1.0);
-  double t = fma(r, 0.2, -0.25);
-  t = fma(r, t, 1.0 / 3.0);
-  t = fma(r, t, -0.5);
-  const double p = fma(r * r, t, r);
-  // (2^52 + 2^31 + k) + (E - 2^52 - 2^31) == E + k exactly
-  const double Ek = __hiloint2double(0x43300000, (int)(0x80000000u ^ (unsigned)k)) + Eoff;
-  return fma(Ek, 0.693147180559945309417232, tb.y + p);
-}
-
-template <typename OutT>
-__device__ __forceinline__ void st_out(OutT *p, double v) {
-  *p = (OutT)v;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -387,18 +330,6 @@ __device__ void producer_warp(const LinParams &P, int ws, int lane, bool left_se
 // ---------------------------------------------------------------------------------------------
 // consumer: log / divide / store, LIN_CONS warps per warp-strip
 // ---------------------------------------------------------------------------------------------
-/* x / d for normal positive operands: MUFU seed + two Newton steps + one correction, no branch */
-__device__ __forceinline__ double div_pos(double x, double d) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-  double e = fma(-d, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-d, r, 1.0);
-  r = fma(r, e, r);
-  double q = x * r;
-  return fma(fma(-d, q, x), r, q);
-}
-
 template <int K, bool HAS_S, bool HAS_V, int RS, typename OutT>
 __device__ void consumer_warp(const LinParams &P, int ws, int cidx, int lane, const double *xring,
                               const double *yring, const double *ering, const int *prod_done, int *cfin,

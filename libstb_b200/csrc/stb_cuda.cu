@@ -15,6 +15,7 @@
 #include "stb_cuda.h"
 #include "fill_mirror.cuh"
 #include "fill_linear.cuh"
+#include "fill_strip.cuh"
 
 static char g_err[512] = "";
 
@@ -40,7 +41,8 @@ struct stb_dev {
   double *s1;           // device copy of column 1 / S1 (capN doubles)
   double *scratch;      // mirror kernel live rows
   size_t scratch_elems;
-  stb::LinearState lin;  // frontier state + hand-off rings of the linear kernel
+  stb::LinearState lin;  // (previous pipeline, kept for A/B runs)
+  stb::StripState strip;  // hand-off rings, counters and tables array of the strip kernel
   float last_ms;
   // staging for host-pointer gathers
   uint32_t *g_n, *g_m;
@@ -94,6 +96,7 @@ extern "C" void stb_cuda_table_destroy(stb_dev_t *d) {
   cudaFree(d->g_m);
   cudaFree(d->g_out);
   stb::linear_state_free(&d->lin);
+  stb::strip_state_free(&d->strip);
   cudaEventDestroy(d->ev0);
   cudaEventDestroy(d->ev1);
   cudaStreamDestroy(d->stream);
@@ -107,7 +110,7 @@ extern "C" size_t stb_cuda_table_ld(const stb_dev_t *d) { return d->ld; }
 extern "C" size_t stb_cuda_table_bytes(const stb_dev_t *d) {
   size_t slab = (size_t)d->capN * d->ld * elem_size(d);
   return slab * (size_t)(d->has_S + d->has_V) + (size_t)d->capN * sizeof(double) +
-         d->scratch_elems * sizeof(double) + stb::linear_state_bytes(&d->lin);
+         d->scratch_elems * sizeof(double) + stb::linear_state_bytes(&d->lin) + stb::strip_state_bytes(&d->strip);
 }
 
 extern "C" int stb_cuda_table_reserve(stb_dev_t *d, unsigned N, unsigned M, int keep) {
@@ -192,21 +195,42 @@ extern "C" int stb_cuda_fill(stb_dev_t *d, double a, unsigned startN, unsigned s
     return -1;
   }
   if (algo == STB_FILL_MIRROR) return fill_mirror(d, a, N, M, s1_host);
-  // linear-domain strip pipeline
-  stb::LinearFillArgs args;
-  args.tabS = d->has_S ? d->S : NULL;
-  args.tabV = d->has_V ? d->V : NULL;
-  args.s1 = d->s1;
-  args.is_float = d->is_float;
-  args.ld = d->ld;
-  args.a = a;
-  args.startN = startN;
-  args.startM = startM;
-  args.N = N;
-  args.M = M;
-  args.num_sms = d->num_sms;
   CK(cudaEventRecord(d->ev0, d->stream));
-  int rc = stb::linear_fill(&d->lin, args, d->stream, d->ev1, g_err, sizeof g_err);
+  int rc;
+  if (getenv("STB_OLD_PIPELINE")) {
+    stb::LinearFillArgs args;
+    args.tabS = d->has_S ? d->S : NULL;
+    args.tabV = d->has_V ? d->V : NULL;
+    args.s1 = d->s1;
+    args.is_float = d->is_float;
+    args.ld = d->ld;
+    args.a = a;
+    args.startN = startN;
+    args.startM = startM;
+    args.N = N;
+    args.M = M;
+    args.num_sms = d->num_sms;
+    rc = stb::linear_fill(&d->lin, args, d->stream, d->ev1, g_err, sizeof g_err);
+  } else {
+    // linear-domain strip pipeline; the whole extent is refilled (startN/startM are an
+    // optimisation the reference has and this path does not need: a refill costs milliseconds)
+    stb::StripTable tb;
+    tb.tabS = d->has_S ? d->S : NULL;
+    tb.tabV = d->has_V ? d->V : NULL;
+    tb.s1 = d->s1;
+    tb.a = a;
+    stb::StripFillArgs args;
+    args.tables = &tb;
+    args.ntables = 1;
+    args.has_S = d->has_S;
+    args.has_V = d->has_V;
+    args.is_float = d->is_float;
+    args.ld = d->ld;
+    args.N = N;
+    args.M = M;
+    args.num_sms = d->num_sms;
+    rc = stb::strip_fill(&d->strip, args, d->stream, d->ev1, g_err, sizeof g_err);
+  }
   if (rc) return rc;
   if (s1_host && d->has_S)
     CK(cudaMemcpyAsync(s1_host, d->s1, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, d->stream));

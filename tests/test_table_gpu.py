@@ -189,14 +189,14 @@ def test_batch_api_matches_scalar():
     t.free()
 
 
-@pytest.mark.parametrize("K", [1, 2, 4])
+@pytest.mark.parametrize("K", [1, 2, 3, 5, 7])
 def test_bit_reproducible_across_geometries(K, monkeypatch):
     """Scaling by powers of two is exact, so the strip width (columns per lane) cannot change
     a single bit of the result."""
     N, M, a = 2000, 700, 0.65
-    monkeypatch.delenv("STB_LINEAR_K", raising=False)
+    monkeypatch.delenv("STB_STRIP_K", raising=False)
     base = stb.Table(N, M, N, M, a, FLAGS)
-    monkeypatch.setenv("STB_LINEAR_K", str(K))
+    monkeypatch.setenv("STB_STRIP_K", str(K))
     t = stb.Table(N, M, N, M, a, FLAGS)
     for which in (0, 1):
         mask = harness.valid_mask(N, M, which == 1)

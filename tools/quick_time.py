@@ -35,13 +35,14 @@ if __name__ == "__main__":
     run(10000, 1000, 0.5, S, label="C1 S")
     run(50000, 5000, 0.7, S, label="C3-shape S")
     run(50000, 5000, 0.7, S | V, label="C3-shape S+V")
-    for k in ("1", "2", "4"):
-        os.environ["STB_LINEAR_K"] = k
+    for k in ("1", "2", "3", "5", "7"):
+        os.environ["STB_STRIP_K"] = k
         run(50000, 5000, 0.7, S, label=f"C3-shape S K={k}")
-    os.environ.pop("STB_LINEAR_K")
+    os.environ.pop("STB_STRIP_K")
     if which != "small":
         run(200000, 20000, 0.7, S, label="C2 S")
         run(200000, 20000, 0.7, S | F, label="C2 S float")
         run(200000, 20000, 0.7, S | V, reps=1, label="C2 S+V")
-    run(2000, 300, 0.7, S | V | stb.S_MIRROR_ORDER, reps=1, label="mirror small")
-    run(10000, 1000, 0.5, S | V | stb.S_MIRROR_ORDER, reps=1, label="mirror C1")
+    if which == "all":
+        run(2000, 300, 0.7, S | V | stb.S_MIRROR_ORDER, reps=1, label="mirror small")
+        run(10000, 1000, 0.5, S | V | stb.S_MIRROR_ORDER, reps=1, label="mirror C1")
