@@ -50,6 +50,9 @@ constexpr int ST_NBR = 32;     // boundary ring (batches) in shared memory
 constexpr int ST_NBG = 256;    // boundary ring (batches) in global memory, per strip boundary
 constexpr int ST_NJ = 32;      // batches of per-lane exponents kept
 constexpr int ST_WARPS = 16;   // warps per CTA
+#ifndef ST_CONS_SLEEP
+#define ST_CONS_SLEEP 40       // ns a consumer sleeps between polls of its batch barrier
+#endif
 constexpr int ST_PRODUCER = 0, ST_LOADER = 4, ST_FLUSHER = 8;  // warp roles; all others consume
 
 struct StripTable {  // one table of a launch
@@ -70,22 +73,39 @@ struct StripParams {
   int *gwritten, *gtaken;  // [boundaries]
   int *abort_flag;
   const LogTabEntry *logtab;
+  int ncons;       // consumer warps in use (tuning knob; at most NB-1)
+  long long *dbg;  // STB_PROFILE_PRODUCER builds: [ctas][8] cycle counters of the producer's phases
 };
 
-template <int K>
+#ifdef STB_PROFILE_PRODUCER
+#define ST_TICK(var) const long long var = clock64()
+#define ST_ACC(slot, t1, t0) dbgacc[slot] += (t1) - (t0)
+#else
+#define ST_TICK(var)
+#define ST_ACC(slot, t1, t0)
+#endif
+
+template <int K, bool HAS_V>
 struct StripCfg {
-  static constexpr int CP = 32 * K;               // row pitch of the x ring (doubles)
-  static constexpr int RS = (K <= 5) ? 128 : 96;  // rows in the x ring
-  static constexpr int NB = RS / ST_B;            // batch slots
+  static constexpr int CP = 32 * K;  // row pitch of the x ring (doubles)
+  // batch slots: as many as fit beside the other shared-memory users, at most 16
+  static constexpr int ROW_BYTES = (CP + (HAS_V ? 32 : 0)) * 8;
+  static constexpr int NB_FIT = (int)((227 * 1024 - 20 * 1024) / ROW_BYTES / ST_B) - 1;
+  static constexpr int NB = NB_FIT > 16 ? 16 : NB_FIT;
+  static constexpr int RS = NB * ST_B;  // ring rows; rows RS..RS+7 duplicate rows 0..7
 };
 
 // ---- shared memory -----------------------------------------------------------------------------
 template <int K, bool HAS_V>
 struct StripSmem {
-  using Cfg = StripCfg<K>;
+  using Cfg = StripCfg<K, HAS_V>;
   LogTabEntry logtab[LOGTAB_N + 1];
-  double xring[Cfg::RS * Cfg::CP];
-  double yring[HAS_V ? Cfg::RS * 32 : 2];
+  // raw x values indexed by producer STEP (not by row): step u of the strip sits in ring row
+  // u % RS, lane l's K columns at [l*K, l*K+K).  Row r of producer lane l was made at step
+  // u = r + l + phi.  Rows RS..RS+7 repeat rows 0..7 so that a consumer's eight consecutive
+  // steps never wrap.
+  double xring[(Cfg::RS + ST_B) * Cfg::CP];
+  double yring[HAS_V ? (Cfg::RS + ST_B) * 32 : 2];
   double ering[ST_NJ * 32];           // (double)E - LOG_EBIAS per (batch, lane)
   double in_x[ST_NBR * ST_B];         // boundary from the left strip
   double out_x[ST_NBR * ST_B];        // boundary for the right strip
@@ -107,10 +127,10 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned 
   unsigned ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)  // suspend-time hint (ns)
       : "memory");
   return ok != 0;
 }
@@ -126,13 +146,21 @@ __device__ __forceinline__ bool mbar_test_wait(unsigned long long *bar, unsigned
   return ok != 0;
 }
 
-/* warp-collective blocking wait; false when the fill was aborted (watchdog / another role) */
+/*
+ * Warp-collective blocking wait; false when the fill was aborted (watchdog / another role).
+ * Polls with the non-blocking test_wait: the blocking try_wait parks the warp in hardware and was
+ * measured to wake late (the hand-off then costs microseconds, not cycles).  SLEEP (ns) between
+ * polls keeps waiting consumer warps from eating the issue slots of working ones.
+ */
+template <int SLEEP>
 __device__ __forceinline__ bool mbar_wait(unsigned long long *bar, unsigned parity, int *abort_flag) {
-  if (mbar_try_wait(bar, parity)) return true;
+  if (mbar_test_wait(bar, parity)) return true;
   const long long t0 = clock64();
   unsigned spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 63u) == 0) {
+  for (;;) {
+    if (SLEEP) __nanosleep(SLEEP);
+    if (mbar_test_wait(bar, parity)) return true;
+    if ((++spins & 1023u) == 0) {
       const int bad = ld_vol(abort_flag) || (clock64() - t0 > FILL_WATCHDOG);
       if (__any_sync(0xffffffffu, bad)) {
         if ((threadIdx.x & 31) == 0) atomicExch(abort_flag, 1);
@@ -140,7 +168,6 @@ __device__ __forceinline__ bool mbar_wait(unsigned long long *bar, unsigned pari
       }
     }
   }
-  return true;
 }
 
 /*
@@ -203,13 +230,55 @@ __device__ __forceinline__ StripGeom strip_geom(const StripParams &P, int strip)
 }
 
 // ---- producer ----------------------------------------------------------------------------------------
+/*
+ * Eight recurrence steps.  x[k]: the lane's K columns; the coefficient of column m_k in row n is
+ * (n-1) - m_k a, formed per step from nm1 = n-1 and ma[k] = m_k a exactly like that (one rounding,
+ * independent of where a strip starts, so every geometry produces the same bits); yin: the left neighbour's value one row up, in this lane's units;
+ * scn: the per-batch factor that brings the neighbour's units to this lane's.  Everything is
+ * stored unconditionally: rows that do not exist (before the strip's first row, past N) land in
+ * ring slots the consumers never read as valid.
+ */
+template <int K, bool HAS_V, bool DUP, int CP, int RS>
+__device__ __forceinline__ void strip_steps(double (&x)[K], const double (&ma)[K], double &nm1, double &yin,
+                                            const double scn,
+                                            const double (&bnd)[ST_B], const bool lane0, const bool write_out,
+                                            double *__restrict__ xr, double *__restrict__ yr,
+                                            double *__restrict__ outp) {
+#pragma unroll
+  for (int i = 0; i < ST_B; i++) {
+    // the left neighbour's last column BEFORE this step's update: its value one row up from
+    // the row this lane makes in the NEXT step
+    double s = shfl_up_d(x[K - 1]);
+    if (lane0) s = bnd[i];
+#pragma unroll
+    for (int k = K - 1; k >= 1; k--) x[k] = fma(nm1 - ma[k], x[k], x[k - 1]);
+    x[0] = fma(nm1 - ma[0], x[0], yin);
+    yin = s * scn;
+    nm1 += 1.0;
+    if (K == 2) {
+      *reinterpret_cast<double2 *>(xr + i * CP) = make_double2(x[0], x[1]);
+      if (DUP) *reinterpret_cast<double2 *>(xr + (RS + i) * CP) = make_double2(x[0], x[1]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        xr[i * CP + k] = x[k];
+        if (DUP) xr[(RS + i) * CP + k] = x[k];
+      }
+    }
+    if (HAS_V) {
+      yr[i * 32] = yin;
+      if (DUP) yr[(RS + i) * 32] = yin;
+    }
+    if (write_out) outp[i] = x[K - 1];
+  }
+}
+
 template <int K, bool HAS_V>
 __device__ void strip_producer(const StripParams &P, StripSmem<K, HAS_V> &sm, const StripGeom &g, int lane,
                                double a, bool has_left, bool has_right, int jlast) {
-  using Cfg = StripCfg<K>;
+  using Cfg = StripCfg<K, HAS_V>;
   constexpr int CP = Cfg::CP, RS = Cfg::RS, NB = Cfg::NB;
   const int L = P.L;
-  const unsigned R = (unsigned)g.R;
 
   double x[K], ma[K];
 #pragma unroll
@@ -217,23 +286,32 @@ __device__ void strip_producer(const StripParams &P, StripSmem<K, HAS_V> &sm, co
     x[k] = 0.0;
     ma[k] = (double)(g.rs + 1 + lane * K + k) * a;
   }
-  // step t = -phi is the first of batch 0; lane l is then at row r = -phi - l, i.e. n = rs+1+r
-  int r = -g.phi - lane;
-  double nm1 = (double)(g.rs + r);  // n - 1
-  int srow = ((r % RS) + RS) % RS;  // ring row of r
+  // step u = 0 (t = -phi) is the first of batch 0; lane l is then at row r = -phi - l, n = rs+1+r
+  double nm1 = (double)(g.rs - g.phi - lane);  // n - 1
   // S^rs_rs = 1 (S^0_0 = 1 for the first strip) seeds the strip's diagonal; with phi > 0 it
   // arrives through the boundary ring like every other row
   double yin = (lane == 0 && (g.phi == 0 || !has_left)) ? 1.0 : 0.0;
   long long E = 0;
   int elow = 0;
   int c_in = -1, c_out = -1;
-  const bool is_last_lane = (lane == L - 1);
+  const bool lane0 = (lane == 0);
+  const bool write_out = has_right && (lane == L - 1);
+  bool slot_free = false;
 
+#ifdef STB_PROFILE_PRODUCER
+  long long dbgacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
   for (int p = 0; p < g.nbatch; ++p) {
+    const int slot = p % NB;
+    ST_TICK(tk0);
     // ---- flow control (uniform across the warp) ----
-    if (p >= NB) {
-      if (!mbar_wait(&sm.empty[p % NB], (unsigned)((p / NB) - 1) & 1u, P.abort_flag)) return;
+    // the ring slot of this batch was probed (non-blocking) one batch ago; consumers are normally
+    // far ahead, so the blocking wait and its latency are rarely needed
+    if (p >= NB && !slot_free) {
+      if (!mbar_wait<0>(&sm.empty[slot], (unsigned)((p / NB) - 1) & 1u, P.abort_flag)) return;
     }
+    if (p + 1 >= NB) slot_free = mbar_test_wait(&sm.empty[(p + 1) % NB], (unsigned)(((p + 1) / NB) - 1) & 1u);
+    ST_TICK(tk1);
     int jb = p + g.delta;
     if (has_left) {
       if (jb > jlast) jb = jlast;
@@ -242,6 +320,7 @@ __device__ void strip_producer(const StripParams &P, StripSmem<K, HAS_V> &sm, co
     if (has_right) {
       if (!ctr_wait<false, 0>(&sm.out_taken, p - ST_NBR, P.abort_flag, c_out)) return;
     }
+    ST_TICK(tk2);
     // ---- renormalise ----
     {
       const int hi = __double2hiint(x[0]);
@@ -259,9 +338,9 @@ __device__ void strip_producer(const StripParams &P, StripSmem<K, HAS_V> &sm, co
     int sE = __shfl_up_sync(0xffffffffu, elow, 1);
     double bnd[ST_B];
     if (has_left) {
-      const int slot = jb & (ST_NBR - 1);
-      if (lane == 0) sE = sm.in_e[slot];
-      const double2 *bp = reinterpret_cast<const double2 *>(&sm.in_x[slot * ST_B]);
+      const int bs = jb & (ST_NBR - 1);
+      if (lane0) sE = sm.in_e[bs];
+      const double2 *bp = reinterpret_cast<const double2 *>(&sm.in_x[bs * ST_B]);
 #pragma unroll
       for (int i = 0; i < ST_B / 2; i++) {
         const double2 v = bp[i];
@@ -269,52 +348,48 @@ __device__ void strip_producer(const StripParams &P, StripSmem<K, HAS_V> &sm, co
         bnd[2 * i + 1] = v.y;
       }
     } else {
-      if (lane == 0) sE = elow;
+      if (lane0) sE = elow;
 #pragma unroll
       for (int i = 0; i < ST_B; i++) bnd[i] = 0.0;
     }
     const double scn = pow2i(sE - elow);
-    if (has_right && is_last_lane) sm.out_e[p & (ST_NBR - 1)] = elow;
+    if (write_out) sm.out_e[p & (ST_NBR - 1)] = elow;
     double *outp = &sm.out_x[(p & (ST_NBR - 1)) * ST_B];
+    double *xr = &sm.xring[slot * ST_B * CP + lane * K];
+    double *yr = &sm.yring[HAS_V ? slot * ST_B * 32 + lane : 0];
 
+    ST_TICK(tk3);
     // ---- eight steps ----
-#pragma unroll
-    for (int i = 0; i < ST_B; i++) {
-      // the left neighbour's last column BEFORE this step's update: its value one row up from
-      // the row this lane computes next
-      double s = shfl_up_d(x[K - 1]);
-      if (lane == 0) s = bnd[i];
-#pragma unroll
-      for (int k = K - 1; k >= 1; k--) x[k] = fma(nm1 - ma[k], x[k], x[k - 1]);
-      x[0] = fma(nm1 - ma[0], x[0], yin);
-      yin = s * scn;
-      nm1 += 1.0;
-      if ((unsigned)r < R) {
-        double *xr = &sm.xring[srow * CP + lane * K];
-        if (K == 2) {
-          *reinterpret_cast<double2 *>(xr) = make_double2(x[0], x[1]);
-        } else {
-#pragma unroll
-          for (int k = 0; k < K; k++) xr[k] = x[k];
-        }
-        if (HAS_V) sm.yring[srow * 32 + lane] = yin;
-      }
-      if (has_right && is_last_lane) outp[i] = x[K - 1];
-      r++;
-      srow = (srow + 1 == RS) ? 0 : srow + 1;
-    }
+    if (slot == 0)
+      strip_steps<K, HAS_V, true, CP, RS>(x, ma, nm1, yin, scn, bnd, lane0, write_out, xr, yr, outp);
+    else
+      strip_steps<K, HAS_V, false, CP, RS>(x, ma, nm1, yin, scn, bnd, lane0, write_out, xr, yr, outp);
+
+    ST_TICK(tk4);
     // ---- publish ----
     __syncwarp();
     asm volatile("" ::: "memory");
-    if (lane == 0) {
+    if (lane0) {
       const int q = p - g.D;
       if (q >= 0 && q < g.QT) mbar_arrive(&sm.full[q % NB]);
       if (has_left) st_vol(&sm.in_taken, p + g.delta);
     }
-    if (has_right && is_last_lane) st_vol(&sm.out_written, p);
+    if (write_out) st_vol(&sm.out_written, p);
+    ST_TICK(tk5);
+    ST_ACC(0, tk1, tk0);  // wait: ring slot free
+    ST_ACC(1, tk2, tk1);  // wait: boundary in / out
+    ST_ACC(2, tk3, tk2);  // renormalise + batch set-up
+    ST_ACC(3, tk4, tk3);  // eight steps
+    ST_ACC(4, tk5, tk4);  // publish
   }
+#ifdef STB_PROFILE_PRODUCER
+  if (lane0 && P.dbg) {
+    for (int i = 0; i < 5; i++) P.dbg[(size_t)blockIdx.x * 8 + i] = dbgacc[i];
+    P.dbg[(size_t)blockIdx.x * 8 + 5] = g.nbatch;
+  }
+#endif
   // a partial last row batch never sees its eighth row: release it now that every row exists
-  if (lane == 0) {
+  if (lane0) {
     const int qd = g.nbatch - 1 - g.D;
     for (int q = (qd < 0 ? 0 : qd + 1); q < g.QT; q++) mbar_arrive(&sm.full[q % NB]);
   }
@@ -324,8 +399,8 @@ __device__ void strip_producer(const StripParams &P, StripSmem<K, HAS_V> &sm, co
 template <int K, bool HAS_S, bool HAS_V, typename OutT>
 __device__ void strip_consumer(const StripParams &P, StripSmem<K, HAS_V> &sm, const StripGeom &g, int lane,
                                const StripTable &tb) {
-  using Cfg = StripCfg<K>;
-  constexpr int CP = Cfg::CP, NB = Cfg::NB;
+  using Cfg = StripCfg<K, HAS_V>;
+  constexpr int CP = Cfg::CP, NB = Cfg::NB, RS = Cfg::RS;
   const int M = P.M;
   int cvalid = M - g.rs;  // columns of this strip that exist
   if (cvalid > P.C) cvalid = P.C;
@@ -339,11 +414,12 @@ __device__ void strip_consumer(const StripParams &P, StripSmem<K, HAS_V> &sm, co
     q = __shfl_sync(0xffffffffu, q, 0);
     if (q >= g.QT) break;
     const int slot = q % NB;
-    if (!mbar_wait(&sm.full[slot], (unsigned)(q / NB) & 1u, P.abort_flag)) return;
+    if (!mbar_wait<ST_CONS_SLEEP>(&sm.full[slot], (unsigned)(q / NB) & 1u, P.abort_flag)) return;
     const int r0 = q * ST_B;
-    const int slot0 = slot * ST_B;
     const bool fast = (r0 >= cvalid - 1) && (r0 + ST_B <= g.R);
-#pragma unroll
+    // not unrolled: the body is ~250 instructions; K copies of it overflow the instruction cache
+    // and the misses stall every warp of the SM, the producer included
+#pragma unroll 1
     for (int kk = 0; kk < K; kk++) {
       if (32 * kk >= cvalid) break;
       const int col = lane + 32 * kk;
@@ -351,13 +427,17 @@ __device__ void strip_consumer(const StripParams &P, StripSmem<K, HAS_V> &sm, co
       const int kq = col % K;
       const bool lane_ok = col < cvalid;
       const size_t cell0 = (size_t)(g.rs + r0) * P.ld + (size_t)(g.rs + col);  // row n-1 = rs+r, column m-1
-      // exponent of producer lane pl at the steps that made rows r0..r0+7: it changes once
+      // producer lane pl made rows r0..r0+7 at steps toff..toff+7 (ring rows ub..ub+7, never
+      // wrapping thanks to the duplicate rows); its exponent changes once on the way
       const int toff = r0 + pl + g.phi;
       const int j0 = toff >> 3, thr = ST_B - (toff & 7);
+      const int ub = (j0 % NB) * ST_B + (toff & 7);
+      const double *xc = &sm.xring[ub * CP + col];
+      const double *yc = &sm.yring[HAS_V ? ub * 32 + pl : 0];
       if (fast) {
         double xv[ST_B];
 #pragma unroll
-        for (int i = 0; i < ST_B; i++) xv[i] = sm.xring[(slot0 + i) * CP + col];
+        for (int i = 0; i < ST_B; i++) xv[i] = xc[i * CP];
         if (HAS_S) {
           const double Ea = sm.ering[(j0 & (ST_NJ - 1)) * 32 + pl];
           const double Eb = sm.ering[((j0 + 1) & (ST_NJ - 1)) * 32 + pl];
@@ -378,7 +458,7 @@ __device__ void strip_consumer(const StripParams &P, StripSmem<K, HAS_V> &sm, co
           double den[ST_B];
 #pragma unroll
           for (int i = 0; i < ST_B; i++)
-            den[i] = (kq == 0) ? sm.yring[(slot0 + i) * 32 + pl] : sm.xring[(slot0 + i) * CP + col - 1];
+            den[i] = (kq == 0) ? yc[i * 32] : xc[i * CP - 1];
           if (lane_ok && !(first_strip && col == 0)) {
             OutT *pV = tabV + cell0;
 #pragma unroll
@@ -390,7 +470,7 @@ __device__ void strip_consumer(const StripParams &P, StripSmem<K, HAS_V> &sm, co
         for (int i = 0; i < ST_B; i++) {
           const int r = r0 + i;
           if (r >= g.R || col > r) continue;
-          const double xv = sm.xring[(slot0 + i) * CP + col];
+          const double xv = xc[i * CP];
           const size_t off = cell0 + (size_t)i * P.ld;
           if (HAS_S) {
             const int j = (r + pl + g.phi) >> 3;
@@ -399,7 +479,7 @@ __device__ void strip_consumer(const StripParams &P, StripSmem<K, HAS_V> &sm, co
             if (first_strip && col == 0) tb.s1[r] = v;
           }
           if (HAS_V && !(first_strip && col == 0)) {
-            const double den = (kq == 0) ? sm.yring[(slot0 + i) * 32 + pl] : sm.xring[(slot0 + i) * CP + col - 1];
+            const double den = (kq == 0) ? yc[i * 32] : xc[i * CP - 1];
             st_out(tabV + off, div_pos(xv, den));
           }
         }
@@ -476,7 +556,7 @@ __device__ void strip_flusher(const StripParams &P, StripSmem<K, HAS_V> &sm, con
 template <int K, bool HAS_S, bool HAS_V, typename OutT>
 __global__ void __launch_bounds__(ST_WARPS * 32, 1) fill_strip_kernel(const StripParams P) {
   using SM = StripSmem<K, HAS_V>;
-  using Cfg = StripCfg<K>;
+  using Cfg = StripCfg<K, HAS_V>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SM &sm = *reinterpret_cast<SM *>(smem_raw);
   const int table = blockIdx.x / P.P, strip = blockIdx.x % P.P;
@@ -509,8 +589,10 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 1) fill_strip_kernel(const Stri
     if (has_right) strip_flusher<K, HAS_V>(P, sm, g, lane, table * P.P + strip);
   } else {
     // a waiter may be at most one phase ahead of its mbarrier: fewer claimants than batch slots
-    const int cidx = warp - 1 - (warp > ST_LOADER) - (warp > ST_FLUSHER);
-    if (cidx < Cfg::NB - 1) strip_consumer<K, HAS_S, HAS_V, OutT>(P, sm, g, lane, tb);
+    // consumers stay off the producer's SM sub-partition (warp % 4 == 0): it keeps its issue slots
+    // and FP64 pipe to itself
+    const int cidx = (warp >> 2) * 3 + (warp & 3) - 1;
+    if ((warp & 3) != 0 && cidx < Cfg::NB - 1 && cidx < P.ncons) strip_consumer<K, HAS_S, HAS_V, OutT>(P, sm, g, lane, tb);
   }
 }
 
@@ -523,6 +605,8 @@ struct StripState {
   LogTabEntry *logtab;
   StripTable *tables;  // device array
   int tables_cap;
+  int ncons;       // consumer warps in use (tuning knob; at most NB-1)
+  long long *dbg;  // STB_PROFILE_PRODUCER builds only
 };
 
 inline void strip_state_free(StripState *st) {
@@ -531,6 +615,7 @@ inline void strip_state_free(StripState *st) {
   cudaFree(st->gctr);
   cudaFree(st->logtab);
   cudaFree(st->tables);
+  cudaFree(st->dbg);
   memset(st, 0, sizeof *st);
 }
 
@@ -685,6 +770,14 @@ inline int strip_fill(StripState *st, const StripFillArgs &A, cudaStream_t strea
   P.gtaken = st->gctr + st->cap;
   P.abort_flag = st->gctr + 2 * st->cap;
   P.logtab = st->logtab;
+  P.ncons = 64;
+  if (const char *s = getenv("STB_STRIP_CONS")) P.ncons = atoi(s);
+  P.dbg = NULL;
+#ifdef STB_PROFILE_PRODUCER
+  if (!st->dbg) cudaMalloc(&st->dbg, 256 * 8 * sizeof(long long));
+  cudaMemsetAsync(st->dbg, 0, 256 * 8 * sizeof(long long), stream);
+  P.dbg = st->dbg;
+#endif
   for (int t0 = 0; t0 < A.ntables && e == cudaSuccess; t0 += per_launch) {
     const int nt = (A.ntables - t0 < per_launch) ? A.ntables - t0 : per_launch;
     P.tables = st->tables + t0;
@@ -706,6 +799,20 @@ inline int strip_fill(StripState *st, const StripFillArgs &A, cudaStream_t strea
       if (t0 + per_launch >= A.ntables) cudaEventRecord(ev_end, stream);
       e = cudaMemcpyAsync(&flag, P.abort_flag, sizeof(int), cudaMemcpyDeviceToHost, stream);
       if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+#ifdef STB_PROFILE_PRODUCER
+      if (e == cudaSuccess && getenv("STB_PROFILE_PRINT")) {
+        static long long h[256 * 8];
+        cudaMemcpy(h, st->dbg, sizeof h, cudaMemcpyDeviceToHost);
+        const int show[4] = {0, 1, nctas / 2, nctas - 1};
+        for (int si = 0; si < 4; si++) {
+          const int c = show[si];
+          if (c < 0 || c >= nctas || c >= 256 || (si && c == show[si - 1])) continue;
+          const double nb = (double)h[c * 8 + 5];
+          fprintf(stderr, "cta %3d batches %6.0f cycles/batch: slot-wait %.0f ring-wait %.0f setup %.0f steps %.0f publish %.0f\n",
+                  c, nb, h[c * 8 + 0] / nb, h[c * 8 + 1] / nb, h[c * 8 + 2] / nb, h[c * 8 + 3] / nb, h[c * 8 + 4] / nb);
+        }
+      }
+#endif
       if (e == cudaSuccess && flag) {
         snprintf(err, errlen, "strip_fill: pipeline watchdog fired (K=%d L=%d P=%d tables/launch=%d)", pl.K, pl.L,
                  pl.P, per_launch);

@@ -31,11 +31,17 @@ def run(N, M, a, flags, reps=3, label=""):
 if __name__ == "__main__":
     S, V, F = stb.S_STABLE, stb.S_UVTABLE, stb.S_FLOAT
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which == "shape":  # python tools/quick_time.py shape N M [a] [flags]
+        N, M = int(sys.argv[2]), int(sys.argv[3])
+        a = float(sys.argv[4]) if len(sys.argv) > 4 else 0.7
+        fl = int(sys.argv[5]) if len(sys.argv) > 5 else S
+        run(N, M, a, fl, label=f"K={os.environ.get('STB_STRIP_K', 'auto')} L={os.environ.get('STB_STRIP_L', 'auto')}")
+        sys.exit(0)
     run(10000, 1000, 0.5, S | V, label="C1 S+V")
     run(10000, 1000, 0.5, S, label="C1 S")
     run(50000, 5000, 0.7, S, label="C3-shape S")
     run(50000, 5000, 0.7, S | V, label="C3-shape S+V")
-    for k in ("1", "2", "3", "5", "7"):
+    for k in ("2", "3", "5", "7"):
         os.environ["STB_STRIP_K"] = k
         run(50000, 5000, 0.7, S, label=f"C3-shape S K={k}")
     os.environ.pop("STB_STRIP_K")
