@@ -320,7 +320,7 @@ def run_own(args):
                     "ms_per_step": 1e3 * wall / args.steps},
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "stb::fill_linear_kernel",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "stb::fill_strip_kernel",
                          "kernel_ms": kern_ms,
                          "fp64_pipe": {"note": "second bound, see DESIGN.md", "cells_per_s": cells / (kern_ms * 1e-3)}},
             "clocks": clocks,

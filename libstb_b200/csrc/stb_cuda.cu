@@ -3,7 +3,7 @@
  *
  * Replaces the allocation part of S_make (lib/stable.c:155-304: ragged row pointers, one
  * malloc per row) by ONE dense row-major slab per table in HBM, and S_remake_part's two
- * double loops (lib/stable.c:356-388, 451-482) by the kernels in fill_linear.cuh /
+ * double loops (lib/stable.c:356-388, 451-482) by the kernels in fill_strip.cuh /
  * fill_mirror.cuh.  sm_100a only; no CPU path.
  */
 #include <cuda_runtime.h>
@@ -14,7 +14,6 @@
 
 #include "stb_cuda.h"
 #include "fill_mirror.cuh"
-#include "fill_linear.cuh"
 #include "fill_strip.cuh"
 
 static char g_err[512] = "";
@@ -41,7 +40,6 @@ struct stb_dev {
   double *s1;           // device copy of column 1 / S1 (capN doubles)
   double *scratch;      // mirror kernel live rows
   size_t scratch_elems;
-  stb::LinearState lin;  // (previous pipeline, kept for A/B runs)
   stb::StripState strip;  // hand-off rings, counters and tables array of the strip kernel
   float last_ms;
   // staging for host-pointer gathers
@@ -95,7 +93,6 @@ extern "C" void stb_cuda_table_destroy(stb_dev_t *d) {
   cudaFree(d->g_n);
   cudaFree(d->g_m);
   cudaFree(d->g_out);
-  stb::linear_state_free(&d->lin);
   stb::strip_state_free(&d->strip);
   cudaEventDestroy(d->ev0);
   cudaEventDestroy(d->ev1);
@@ -110,7 +107,7 @@ extern "C" size_t stb_cuda_table_ld(const stb_dev_t *d) { return d->ld; }
 extern "C" size_t stb_cuda_table_bytes(const stb_dev_t *d) {
   size_t slab = (size_t)d->capN * d->ld * elem_size(d);
   return slab * (size_t)(d->has_S + d->has_V) + (size_t)d->capN * sizeof(double) +
-         d->scratch_elems * sizeof(double) + stb::linear_state_bytes(&d->lin) + stb::strip_state_bytes(&d->strip);
+         d->scratch_elems * sizeof(double) + stb::strip_state_bytes(&d->strip);
 }
 
 extern "C" int stb_cuda_table_reserve(stb_dev_t *d, unsigned N, unsigned M, int keep) {
@@ -197,21 +194,7 @@ extern "C" int stb_cuda_fill(stb_dev_t *d, double a, unsigned startN, unsigned s
   if (algo == STB_FILL_MIRROR) return fill_mirror(d, a, N, M, s1_host);
   CK(cudaEventRecord(d->ev0, d->stream));
   int rc;
-  if (getenv("STB_OLD_PIPELINE")) {
-    stb::LinearFillArgs args;
-    args.tabS = d->has_S ? d->S : NULL;
-    args.tabV = d->has_V ? d->V : NULL;
-    args.s1 = d->s1;
-    args.is_float = d->is_float;
-    args.ld = d->ld;
-    args.a = a;
-    args.startN = startN;
-    args.startM = startM;
-    args.N = N;
-    args.M = M;
-    args.num_sms = d->num_sms;
-    rc = stb::linear_fill(&d->lin, args, d->stream, d->ev1, g_err, sizeof g_err);
-  } else {
+  {
     // linear-domain strip pipeline; the whole extent is refilled (startN/startM are an
     // optimisation the reference has and this path does not need: a refill costs milliseconds)
     stb::StripTable tb;

@@ -189,7 +189,7 @@ def test_batch_api_matches_scalar():
     t.free()
 
 
-@pytest.mark.parametrize("K", [1, 2, 3, 5, 7])
+@pytest.mark.parametrize("K", [1, 3, 5, 7])
 def test_bit_reproducible_across_geometries(K, monkeypatch):
     """Scaling by powers of two is exact, so the strip width (columns per lane) cannot change
     a single bit of the result."""

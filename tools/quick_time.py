@@ -41,7 +41,7 @@ if __name__ == "__main__":
     run(10000, 1000, 0.5, S, label="C1 S")
     run(50000, 5000, 0.7, S, label="C3-shape S")
     run(50000, 5000, 0.7, S | V, label="C3-shape S+V")
-    for k in ("2", "3", "5", "7"):
+    for k in ("1", "3", "5", "7"):
         os.environ["STB_STRIP_K"] = k
         run(50000, 5000, 0.7, S, label=f"C3-shape S K={k}")
     os.environ.pop("STB_STRIP_K")

@@ -39,8 +39,10 @@ __global__ void steps_kernel(long long *cycles, double *sink, int batches, doubl
     if (lane == 0) sE = elow;
     const double scn = pow2i(sE - elow);
     const int slot = p & 1;
-    strip_steps<K, HAS_V, false, CP, RS>(x, ma, nm1, yin, scn, bnd, lane == 0, lane == 31, xring + slot * 8 * CP + lane * K,
-                                         yring + slot * 8 * 32 + lane, outx);
+    strip_steps<K, HAS_V, false, CP, RS, ST_RB>(x, ma, nm1, yin, scn, bnd, lane == 0, lane == 31,
+                                                xring + slot * 8 * CP + lane * K, yring + slot * 8 * 32 + lane, outx);
+    strip_steps<K, HAS_V, false, CP, RS, ST_RB>(x, ma, nm1, yin, scn, bnd + ST_RB, lane == 0, lane == 31,
+                                                xring + slot * 8 * CP + lane * K, yring + slot * 8 * 32 + lane, outx + ST_RB);
   }
   long long t1 = clock64();
   if (lane == 0) cycles[blockIdx.x * (blockDim.x >> 5) + warp] = t1 - t0;
@@ -62,7 +64,7 @@ void run(int warps, int batches) {
   if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); exit(1); }
   long long h[32];
   cudaMemcpy(h, cyc, warps * sizeof(long long), cudaMemcpyDeviceToHost);
-  double per_step = (double)h[0] / batches / 8.0;
+  double per_step = (double)h[0] / batches / (double)ST_B;
   printf("K=%d V=%d warps/SM=%d : %.1f cycles/step/warp  -> %.2f cycles per cell per SM\n", K, (int)HAS_V, warps, per_step,
          per_step / (32.0 * K * warps));
   cudaFree(cyc);
