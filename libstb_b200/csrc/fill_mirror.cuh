@@ -7,7 +7,7 @@
  *   - V uses only + - * /  =>  bit-identical to the CPU library.
  *   - S goes through logadd (lib/stable.c:95-103): max + log(1.0 + exp(min - max)), plain log,
  *     not log1p.  CUDA's log/exp differ from glibc's by <= 1 ulp, so S agrees to a few ulps.
- * It is the parity gate for the fast kernel in fill_linear.cuh and the "exact" mode of the
+ * It is the parity gate for the fast kernel in fill_strip.cuh and the "exact" mode of the
  * product; it is latency-bound by design (one dependent exp->log chain per row) and is not the
  * throughput path.
  *
