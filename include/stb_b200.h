@@ -45,6 +45,27 @@ int stb_extend(stable_t *sp, unsigned N, unsigned M);
  */
 int stb_read_rows(stable_t *sp, int which_V, unsigned n0, unsigned nrows, double *dst);
 
+/*
+ * Discount sweep -- the batched form of "S_remake(sp, a) then look up my statistics" that
+ * samplea's log-posterior does once per evaluation (lib/samplea.c:57-82).  For every discount
+ * a[j] a full N x M log S table is filled on the device (several tables side by side per
+ * launch, streamed through a few resident slabs) and reduced to what the caller asked for:
+ *   gather_out [na][npairs]  S_S(n[i], m[i]) at a[j]      (NULL: not wanted)
+ *   sum_out    [na]          sum_i of those values         (NULL: not wanted)
+ *   lastrow_out[na][M]       log S^N_m, m = 1..M           (NULL: not wanted)
+ * S_S conventions apply to the pairs (n==m -> 0, m==1 -> log S^n_1, m==0 or n<m or beyond N/M
+ * -> -HUGE_VAL).  All pointers are HOST pointers.  flags: 0 or S_FLOAT.  Returns non-zero on error.
+ */
+typedef struct stb_sweep stb_sweep_t;
+stb_sweep_t *stb_sweep_create(unsigned N, unsigned M, uint32_t flags);
+int stb_sweep_set_pairs(stb_sweep_t *w, const uint32_t *n, const uint32_t *m, size_t npairs);
+int stb_sweep_run(stb_sweep_t *w, const double *a, size_t na, double *gather_out, double *sum_out,
+                  double *lastrow_out);
+/* device milliseconds the fill kernels of the most recent stb_sweep_run took; tables filled per launch */
+double stb_sweep_last_fill_ms(const stb_sweep_t *w);
+int stb_sweep_tables_in_flight(const stb_sweep_t *w);
+void stb_sweep_free(stb_sweep_t *w);
+
 /* device milliseconds of the most recent fill (CUDA events around the kernel) */
 double stb_last_fill_ms(const stable_t *sp);
 /* device address and row pitch (elements) of the S (which_V==0) or V slab; cell (n,m) at [(n-1)*ld+m-1] */

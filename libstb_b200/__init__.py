@@ -51,6 +51,12 @@ def lib() -> C.CDLL:
         f.restype, f.argtypes = C.c_int, [vp, vp, vp, vp, C.c_size_t]
     L.stb_extend.restype, L.stb_extend.argtypes = C.c_int, [vp, u, u]
     L.stb_read_rows.restype, L.stb_read_rows.argtypes = C.c_int, [vp, C.c_int, u, u, dp]
+    L.stb_sweep_create.restype, L.stb_sweep_create.argtypes = vp, [u, u, C.c_uint32]
+    L.stb_sweep_set_pairs.restype, L.stb_sweep_set_pairs.argtypes = C.c_int, [vp, u32p, u32p, C.c_size_t]
+    L.stb_sweep_run.restype, L.stb_sweep_run.argtypes = C.c_int, [vp, dp, C.c_size_t, dp, dp, dp]
+    L.stb_sweep_last_fill_ms.restype, L.stb_sweep_last_fill_ms.argtypes = d, [vp]
+    L.stb_sweep_tables_in_flight.restype, L.stb_sweep_tables_in_flight.argtypes = C.c_int, [vp]
+    L.stb_sweep_free.restype, L.stb_sweep_free.argtypes = None, [vp]
     L.stb_last_fill_ms.restype, L.stb_last_fill_ms.argtypes = d, [vp]
     L.stb_device_table.restype, L.stb_device_table.argtypes = vp, [vp, C.c_int, C.POINTER(C.c_size_t)]
     L.stb_device_count.restype, L.stb_device_count.argtypes = C.c_int, []
@@ -136,6 +142,53 @@ class Table:
         if self.sp:
             self._L.S_free(self.sp)
             self.sp = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Sweep:
+    """A discount sweep context (include/stb_b200.h: stb_sweep_*).  Every method is one C-ABI call."""
+
+    def __init__(self, N, M, flags=0):
+        self._L = lib()
+        self.N, self.M = N, M
+        self.w = self._L.stb_sweep_create(N, M, flags)
+        if not self.w:
+            raise RuntimeError("stb_sweep_create failed: " + self._L.stb_last_error().decode())
+        self.npairs = 0
+
+    def set_pairs(self, n, m):
+        n = np.ascontiguousarray(n, dtype=np.uint32)
+        m = np.ascontiguousarray(m, dtype=np.uint32)
+        u32p = C.POINTER(C.c_uint32)
+        if self._L.stb_sweep_set_pairs(self.w, n.ctypes.data_as(u32p), m.ctypes.data_as(u32p), n.shape[0]):
+            raise RuntimeError("stb_sweep_set_pairs failed: " + self._L.stb_last_error().decode())
+        self.npairs = n.shape[0]
+
+    def run(self, a, gather=True, sums=True, lastrow=False):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        dp = C.POINTER(C.c_double)
+        g = np.empty((a.shape[0], self.npairs)) if gather else None
+        s = np.empty(a.shape[0]) if sums else None
+        r = np.empty((a.shape[0], self.M)) if lastrow else None
+        ptr = lambda x: x.ctypes.data_as(dp) if x is not None else None
+        if self._L.stb_sweep_run(self.w, a.ctypes.data_as(dp), a.shape[0], ptr(g), ptr(s), ptr(r)):
+            raise RuntimeError("stb_sweep_run failed: " + self._L.stb_last_error().decode())
+        return g, s, r
+
+    @property
+    def last_fill_ms(self): return self._L.stb_sweep_last_fill_ms(self.w)
+    @property
+    def tables_in_flight(self): return self._L.stb_sweep_tables_in_flight(self.w)
+
+    def free(self):
+        if self.w:
+            self._L.stb_sweep_free(self.w)
+            self.w = None
 
     def __del__(self):
         try:

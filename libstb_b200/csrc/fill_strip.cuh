@@ -867,6 +867,13 @@ inline bool strip_plan(unsigned M, int slots, size_t elem_size, StripPlan *pl) {
   return false;
 }
 
+/* tables one launch fills side by side: each gets the CTAs its widest shape needs */
+inline int strip_tables_per_launch(unsigned M, int num_sms) {
+  int pmin = (int)((M + 32u * 7u - 1) / (32u * 7u));
+  int per_launch = num_sms / (pmin > 0 ? pmin : 1);
+  return per_launch < 1 ? 1 : per_launch;
+}
+
 struct StripFillArgs {
   const StripTable *tables;  // HOST array of ntables entries
   int ntables;
@@ -890,9 +897,7 @@ inline int strip_fill(StripState *st, const StripFillArgs &A, cudaStream_t strea
   StripPlan pl;
   int per_launch = 1;
   if (A.ntables > 1) {
-    int pmin = (int)((A.M + 32u * 7u - 1) / (32u * 7u));
-    per_launch = A.num_sms / (pmin > 0 ? pmin : 1);
-    if (per_launch < 1) per_launch = 1;
+    per_launch = strip_tables_per_launch(A.M, A.num_sms);
     if (per_launch > A.ntables) per_launch = A.ntables;
   }
   if (!strip_plan(A.M, A.num_sms / per_launch, A.is_float ? 4 : 8, &pl)) {

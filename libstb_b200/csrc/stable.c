@@ -486,6 +486,39 @@ int stb_V_batch_device(stable_t *sp, const uint32_t *n, const uint32_t *m, doubl
   return batch(sp, STB_TAB_V, n, m, out, count, 1);
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* discount sweep (stb_b200.h)                                                                 */
+/* ------------------------------------------------------------------------------------------ */
+struct stb_sweep {
+  stb_sweep_dev_t *dev;
+  float last_ms;
+};
+
+stb_sweep_t *stb_sweep_create(unsigned N, unsigned M, uint32_t flags) {
+  stb_sweep_t *w = (stb_sweep_t *)calloc(1, sizeof *w);
+  if (!w) return NULL;
+  w->dev = stb_cuda_sweep_create(N, M, (flags & S_FLOAT) != 0);
+  if (!w->dev) {
+    free(w);
+    return NULL;
+  }
+  return w;
+}
+int stb_sweep_set_pairs(stb_sweep_t *w, const uint32_t *n, const uint32_t *m, size_t npairs) {
+  return w ? stb_cuda_sweep_set_pairs(w->dev, n, m, npairs) : 1;
+}
+int stb_sweep_run(stb_sweep_t *w, const double *a, size_t na, double *gather_out, double *sum_out,
+                  double *lastrow_out) {
+  return w ? stb_cuda_sweep_run(w->dev, a, na, gather_out, sum_out, lastrow_out, &w->last_ms) : 1;
+}
+double stb_sweep_last_fill_ms(const stb_sweep_t *w) { return w->last_ms; }
+int stb_sweep_tables_in_flight(const stb_sweep_t *w) { return stb_cuda_sweep_tables_in_flight(w->dev); }
+void stb_sweep_free(stb_sweep_t *w) {
+  if (!w) return;
+  stb_cuda_sweep_destroy(w->dev);
+  free(w);
+}
+
 int stb_extend(stable_t *sp, unsigned N, unsigned M) {
   if (!sp || N > sp->maxN || M > sp->maxM) return 1;
   if (N <= sp->usedN && M <= sp->usedM) return 0;

@@ -12,6 +12,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include "stb_cuda.h"
 #include "fill_mirror.cuh"
 #include "fill_strip.cuh"
@@ -313,6 +315,231 @@ extern "C" int stb_cuda_gather(stb_dev_t *d, int which, unsigned usedN, unsigned
   if (!on_device)
     CK(cudaMemcpyAsync(out, d->g_out, count * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
   CK(cudaStreamSynchronize(d->stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// discount sweep
+// ---------------------------------------------------------------------------------------------
+struct stb_sweep_dev {
+  int device, num_sms;
+  cudaStream_t stream;
+  cudaEvent_t ev0, ev1;
+  unsigned N, M;
+  int is_float;
+  size_t ld;
+  int T;               // slabs == tables per launch
+  void *slab;          // [T][N][ld]
+  double *s1;          // [T][N]
+  stb::StripState strip;
+  uint32_t *d_n, *d_m;
+  size_t npairs;
+  double *d_gather;    // [T][npairs]
+  double *d_partial;   // [T][nblk]
+  double *d_sum;       // [T]
+  double *h_stage;     // pinned staging for sums
+};
+
+/* S_S conventions (lib/stable.c:941-949) on a dense slab; partial sums per block in a fixed order */
+template <typename T>
+__global__ void sweep_gather_kernel(const T *__restrict__ slabs, size_t slab_elems, size_t ld, unsigned N, unsigned M,
+                                    const uint32_t *__restrict__ n, const uint32_t *__restrict__ m, size_t npairs,
+                                    double *__restrict__ gather, double *__restrict__ partial) {
+  __shared__ double red[256];
+  const int tb = blockIdx.y;
+  const T *tab = slabs + (size_t)tb * slab_elems;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.0;
+  if (i < npairs) {
+    const unsigned nn = n[i], mm = m[i];
+    if (nn == mm)
+      v = 0.0;
+    else if (mm == 0 || nn < mm || nn > N || mm > M)
+      v = -HUGE_VAL;
+    else
+      v = (double)tab[(size_t)(nn - 1) * ld + (mm - 1)];
+    if (gather) gather[(size_t)tb * npairs + i] = v;
+  }
+  red[threadIdx.x] = v;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[(size_t)tb * gridDim.x + blockIdx.x] = red[0];
+}
+
+__global__ void sweep_sum_kernel(const double *__restrict__ partial, int nblk, double *__restrict__ sum) {
+  __shared__ double red[256];
+  const int tb = blockIdx.x;
+  double v = 0.0;
+  for (int b = threadIdx.x; b < nblk; b += 256) v += partial[(size_t)tb * nblk + b];
+  red[threadIdx.x] = v;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sum[tb] = red[0];
+}
+
+extern "C" void stb_cuda_sweep_destroy(stb_sweep_dev_t *w) {
+  if (!w) return;
+  cudaSetDevice(w->device);
+  if (w->stream) cudaStreamSynchronize(w->stream);
+  cudaFree(w->slab);
+  cudaFree(w->s1);
+  cudaFree(w->d_n);
+  cudaFree(w->d_m);
+  cudaFree(w->d_gather);
+  cudaFree(w->d_partial);
+  cudaFree(w->d_sum);
+  if (w->h_stage) cudaFreeHost(w->h_stage);
+  stb::strip_state_free(&w->strip);
+  if (w->ev0) cudaEventDestroy(w->ev0);
+  if (w->ev1) cudaEventDestroy(w->ev1);
+  if (w->stream) cudaStreamDestroy(w->stream);
+  free(w);
+}
+
+extern "C" stb_sweep_dev_t *stb_cuda_sweep_create(unsigned N, unsigned M, int is_float) {
+  if (stb_cuda_device_count() <= 0) {
+    if (!g_err[0]) snprintf(g_err, sizeof g_err, "no CUDA device");
+    return NULL;
+  }
+  if (M < 1 || M > N) {
+    snprintf(g_err, sizeof g_err, "stb_cuda_sweep_create: bad extent %ux%u", N, M);
+    return NULL;
+  }
+  stb_sweep_dev_t *w = (stb_sweep_dev_t *)calloc(1, sizeof *w);
+  if (!w) return NULL;
+  w->N = N;
+  w->M = M;
+  w->is_float = is_float != 0;
+  w->ld = ((size_t)M + 31) / 32 * 32;
+  cudaError_t e = cudaGetDevice(&w->device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&w->num_sms, cudaDevAttrMultiProcessorCount, w->device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&w->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&w->ev1);
+  if (e == cudaSuccess) {
+    w->T = stb::strip_tables_per_launch(M, w->num_sms);
+    // leave room on the device: never more than a quarter of its memory in slabs
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const size_t per = (size_t)N * w->ld * (is_float ? 4 : 8);
+    while (w->T > 1 && (size_t)w->T * per > free_b / 4) w->T--;
+    e = cudaMalloc(&w->slab, (size_t)w->T * per);
+  }
+  if (e == cudaSuccess) e = cudaMalloc(&w->s1, (size_t)w->T * N * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&w->d_sum, (size_t)w->T * sizeof(double));
+  if (e == cudaSuccess) e = cudaHostAlloc(&w->h_stage, (size_t)w->T * sizeof(double), cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    fail(e, "stb_cuda_sweep_create");
+    stb_cuda_sweep_destroy(w);
+    return NULL;
+  }
+  return w;
+}
+
+extern "C" int stb_cuda_sweep_tables_in_flight(const stb_sweep_dev_t *w) { return w->T; }
+
+extern "C" int stb_cuda_sweep_set_pairs(stb_sweep_dev_t *w, const uint32_t *n, const uint32_t *m, size_t npairs) {
+  CK(cudaSetDevice(w->device));
+  cudaFree(w->d_n);
+  cudaFree(w->d_m);
+  cudaFree(w->d_gather);
+  cudaFree(w->d_partial);
+  w->d_n = w->d_m = NULL;
+  w->d_gather = w->d_partial = NULL;
+  w->npairs = npairs;
+  if (!npairs) return 0;
+  const size_t nblk = (npairs + 255) / 256;
+  CK(cudaMalloc(&w->d_n, npairs * sizeof(uint32_t)));
+  CK(cudaMalloc(&w->d_m, npairs * sizeof(uint32_t)));
+  CK(cudaMalloc(&w->d_gather, (size_t)w->T * npairs * sizeof(double)));
+  CK(cudaMalloc(&w->d_partial, (size_t)w->T * nblk * sizeof(double)));
+  CK(cudaMemcpyAsync(w->d_n, n, npairs * sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
+  CK(cudaMemcpyAsync(w->d_m, m, npairs * sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
+  CK(cudaStreamSynchronize(w->stream));
+  return 0;
+}
+
+extern "C" int stb_cuda_sweep_run(stb_sweep_dev_t *w, const double *a, size_t na, double *gather_out, double *sum_out,
+                                  double *lastrow_out, float *fill_ms) {
+  CK(cudaSetDevice(w->device));
+  const size_t es = w->is_float ? 4 : 8;
+  const size_t slab_elems = (size_t)w->N * w->ld;
+  const int nblk = (int)((w->npairs + 255) / 256);
+  float total_ms = 0.f;
+  if ((gather_out || sum_out) && !w->npairs) {
+    snprintf(g_err, sizeof g_err, "stb_cuda_sweep_run: no look-up pairs set");
+    return -1;
+  }
+  std::vector<stb::StripTable> tabs((size_t)w->T);
+  for (size_t j0 = 0; j0 < na; j0 += (size_t)w->T) {
+    const int nt = (int)((na - j0 < (size_t)w->T) ? na - j0 : (size_t)w->T);
+    for (int t = 0; t < nt; t++) {
+      tabs[t].tabS = (char *)w->slab + (size_t)t * slab_elems * es;
+      tabs[t].tabV = NULL;
+      tabs[t].s1 = w->s1 + (size_t)t * w->N;
+      tabs[t].a = a[j0 + t];
+    }
+    stb::StripFillArgs args;
+    args.tables = tabs.data();
+    args.ntables = nt;
+    args.has_S = 1;
+    args.has_V = 0;
+    args.is_float = w->is_float;
+    args.ld = w->ld;
+    args.N = w->N;
+    args.M = w->M;
+    args.num_sms = w->num_sms;
+    CK(cudaEventRecord(w->ev0, w->stream));
+    int rc = stb::strip_fill(&w->strip, args, w->stream, w->ev1, g_err, sizeof g_err);
+    if (rc) return rc;
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, w->ev0, w->ev1));
+    total_ms += ms;
+    if (gather_out || sum_out) {
+      dim3 grid((unsigned)nblk, (unsigned)nt);
+      if (w->is_float)
+        sweep_gather_kernel<float><<<grid, 256, 0, w->stream>>>((const float *)w->slab, slab_elems, w->ld, w->N, w->M,
+                                                                  w->d_n, w->d_m, w->npairs,
+                                                                  gather_out ? w->d_gather : NULL, w->d_partial);
+      else
+        sweep_gather_kernel<double><<<grid, 256, 0, w->stream>>>((const double *)w->slab, slab_elems, w->ld, w->N,
+                                                                   w->M, w->d_n, w->d_m, w->npairs,
+                                                                   gather_out ? w->d_gather : NULL, w->d_partial);
+      CK(cudaGetLastError());
+      if (sum_out) {
+        sweep_sum_kernel<<<nt, 256, 0, w->stream>>>(w->d_partial, nblk, w->d_sum);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(w->h_stage, w->d_sum, (size_t)nt * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
+      }
+      if (gather_out)
+        CK(cudaMemcpyAsync(gather_out + j0 * w->npairs, w->d_gather, (size_t)nt * w->npairs * sizeof(double),
+                           cudaMemcpyDeviceToHost, w->stream));
+    }
+    if (lastrow_out) {
+      for (int t = 0; t < nt; t++) {
+        const char *row = (const char *)w->slab + ((size_t)t * slab_elems + (size_t)(w->N - 1) * w->ld) * es;
+        if (!w->is_float) {
+          CK(cudaMemcpyAsync(lastrow_out + (j0 + t) * w->M, row, (size_t)w->M * sizeof(double), cudaMemcpyDeviceToHost,
+                             w->stream));
+        } else {
+          std::vector<float> tmp(w->M);
+          CK(cudaMemcpyAsync(tmp.data(), row, (size_t)w->M * sizeof(float), cudaMemcpyDeviceToHost, w->stream));
+          CK(cudaStreamSynchronize(w->stream));
+          for (unsigned c = 0; c < w->M; c++) lastrow_out[(j0 + t) * w->M + c] = (double)tmp[c];
+        }
+      }
+    }
+    CK(cudaStreamSynchronize(w->stream));
+    if (sum_out)
+      for (int t = 0; t < nt; t++) sum_out[j0 + t] = w->h_stage[t];
+  }
+  if (fill_ms) *fill_ms = total_ms;
   return 0;
 }
 

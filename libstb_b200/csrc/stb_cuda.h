@@ -77,6 +77,30 @@ int stb_cuda_read_rows(stb_dev_t *d, int which, unsigned row0, unsigned nrows, d
 int stb_cuda_gather(stb_dev_t *d, int which, unsigned usedN, unsigned usedM, const uint32_t *n,
                     const uint32_t *m, double *out, size_t count, int on_device);
 
+/*
+ * Discount sweep: fill MANY tables of one extent (N x M, log S only), one per discount, and keep
+ * from each only what a caller such as samplea's log-posterior needs (lib/samplea.c:57-82: a
+ * full refill at the new discount, then a sum of S_S(n_ik, t_ik) over the statistics) -- the
+ * values at a fixed set of (n,m) pairs, their sum, and the last row.  The tables themselves are
+ * streamed through a few resident slabs (as many as one launch fills side by side) and
+ * overwritten by the next wave.
+ */
+typedef struct stb_sweep_dev stb_sweep_dev_t;
+stb_sweep_dev_t *stb_cuda_sweep_create(unsigned N, unsigned M, int is_float);
+void stb_cuda_sweep_destroy(stb_sweep_dev_t *w);
+/* the look-up set, HOST arrays; S_S conventions (n==m -> 0, m==0 or n<m -> -inf, beyond N/M -> -inf) */
+int stb_cuda_sweep_set_pairs(stb_sweep_dev_t *w, const uint32_t *n, const uint32_t *m, size_t npairs);
+/*
+ * Run the sweep over a[0..na).  Any of the outputs may be NULL:
+ *   gather_out [na][npairs]  value at each pair;   sum_out [na]  their sum (fixed-order tree);
+ *   lastrow_out [na][M]  row N of each table.
+ * HOST pointers.  *fill_ms receives the device time spent in the fill kernels.
+ */
+int stb_cuda_sweep_run(stb_sweep_dev_t *w, const double *a, size_t na, double *gather_out, double *sum_out,
+                       double *lastrow_out, float *fill_ms);
+/* tables one launch fills side by side for this extent on this device */
+int stb_cuda_sweep_tables_in_flight(const stb_sweep_dev_t *w);
+
 /* raw device pointer of a table (for the batched samplers and for tests) */
 void *stb_cuda_table_ptr(stb_dev_t *d, int which);
 
