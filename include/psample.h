@@ -1,0 +1,100 @@
+/*
+ * psample.h -- posterior samplers for the Pitman-Yor discount a and concentration b.
+ *
+ * Source-compatible with the reference's lib/psample.h (B_MIN/B_MAX :58-59, scnt_int :64,
+ * stcnt_int :68, sampleb :79-84, A_MIN/A_MAX/SQUEEZEA :89-94, samplea :104-110, SliceSimple
+ * :45-51) in its SLICE-SAMPLER configuration (PSAMPLE_ARS undefined): samplea/sampleb run
+ * SliceSimple, not ARS.  samplea's log-posterior refills a Stirling table per evaluation
+ * (lib/samplea.c:57-60); here that refill is the CUDA table engine of stable.h.
+ * The batched forms (thousands of independent chains in lock-step) are in stb_b200.h.
+ */
+#ifndef STB_B200_PSAMPLE_H
+#define STB_B200_PSAMPLE_H
+
+#include <stdint.h>
+
+#include "srng.h"
+#include "stable.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/*
+ * Shrinking-interval slice sampler for a unimodal log-posterior post(x, pars).  *xp: start
+ * (inside bounds) and result.  Returns non-zero on error (start outside the bounds, or 200
+ * proposals without acceptance).  (lib/sslice.c:33-80)
+ */
+int SliceSimple(double *xp, double (*post)(double, void *), double *bounds, rngp_t rng, int loops, void *pars);
+
+#define B_MIN 0.01
+#define B_MAX 2000
+
+typedef uint32_t scnt_int;  /* counts */
+typedef uint16_t stcnt_int; /* table counts */
+
+/*
+ * One MCMC update of the concentration b given the discount apar, gamma(shape, scale) prior,
+ * I restaurants with customer totals N[] and table totals T[].  (lib/sampleb.c:79-159)
+ */
+double sampleb(double b_in, int I, double shape, double scale, scnt_int *N, scnt_int *T, double apar, rngp_t rng,
+               int loops, int verbose);
+
+#define A_MIN 0.01
+#define A_MAX 0.98
+#define SQUEEZEA 0.2
+
+/*
+ * One MCMC update of the discount a (uniform prior on [A_MIN, A_MAX], moves squeezed to
+ * +-SQUEEZEA).  n[i][k], t[i][k]: customers / tables of dish k in restaurant i (k < K[i]), or
+ * the callback getval(&n,&t,i,k) when non-NULL; T[i] = sum_k t[i][k]; bpar[i]: concentration of
+ * restaurant i.  Builds and frees its own Stirling table.  (lib/samplea.c:155-225)
+ */
+double samplea(double apar, int I, int *K, scnt_int *T, scnt_int **n, stcnt_int **t,
+               void (*getval)(scnt_int *n, stcnt_int *t, unsigned i, unsigned k), double *bpar, rngp_t rng,
+               int loops, int verbose);
+
+/* ------------------------------------------------------------------------------------------ */
+/* batched samplers: C independent chains in lock-step, one batched evaluation per round        */
+/* ------------------------------------------------------------------------------------------ */
+
+/*
+ * Per-chain random streams: glibc's 48-bit generator with one state per chain.
+ * stb_rng48_state(seed) is the state srand48(seed) sets; the draw functions advance *state exactly
+ * like drand48 / lrand48 / the distributions of srng.h advance the global state.
+ */
+uint64_t stb_rng48_state(long seed);
+double stb_rng48_drand(uint64_t *state);
+long stb_rng48_lrand48(uint64_t *state);
+double stb_rng48_gaussian(uint64_t *state, double sigma);
+double stb_rng48_gamma(uint64_t *state, double a);
+double stb_rng48_beta(uint64_t *state, double a, double b);
+
+typedef struct stb_sample_stats {
+  uint64_t evals;  /* log-posterior evaluations over all chains */
+  uint64_t rounds; /* lock-step rounds (batched evaluations) */
+  double eval_ms;  /* device milliseconds spent in the evaluations */
+  /* optional trace: chain c's evaluated points / values in order at [c*trace_cap + k], count in trace_n[c] */
+  double *trace_x, *trace_v;
+  uint32_t *trace_n;
+  uint32_t trace_cap;
+} stb_sample_stats;
+
+/*
+ * samplea for C chains over the SAME statistics: a[c] in/out, rng[c] in/out.  bpar: [I], or
+ * [C][I] when bpar_per_chain.  Every round fills one Stirling table per active chain at that
+ * chain's proposed discount (a discount sweep) and reduces it against the statistics.
+ * Returns 0; 1+c when chain c failed like the scalar sampler would exit (start outside
+ * [max(A_MIN, a-SQUEEZEA), A_MAX], 200 rejected proposals); negative on device / memory errors.
+ */
+int stb_samplea_batch(double *a, size_t C, int I, const int *K, const scnt_int *T, scnt_int **n, stcnt_int **t,
+                      const double *bpar, int bpar_per_chain, uint64_t *rng, int loops, stb_sample_stats *st);
+
+/* sampleb for C chains: b[c] in/out, apar[c] the chain's discount, rng[c] in/out */
+int stb_sampleb_batch(double *b, size_t C, int I, double shape, double scale, const scnt_int *N, const scnt_int *T,
+                      const double *apar, uint64_t *rng, int loops, stb_sample_stats *st);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -57,6 +57,29 @@ def lib() -> C.CDLL:
     L.stb_sweep_last_fill_ms.restype, L.stb_sweep_last_fill_ms.argtypes = d, [vp]
     L.stb_sweep_tables_in_flight.restype, L.stb_sweep_tables_in_flight.argtypes = C.c_int, [vp]
     L.stb_sweep_free.restype, L.stb_sweep_free.argtypes = None, [vp]
+    # samplers (include/psample.h, srng.h, digamma.h)
+    u64p, ip = C.POINTER(C.c_uint64), C.POINTER(C.c_int)
+    POST = C.CFUNCTYPE(d, d, vp)
+    L.SliceSimple.restype, L.SliceSimple.argtypes = C.c_int, [dp, POST, dp, vp, C.c_int, vp]
+    L.sampleb.restype, L.sampleb.argtypes = d, [d, C.c_int, d, d, u32p, u32p, d, vp, C.c_int, C.c_int]
+    L.samplea.restype = d
+    L.samplea.argtypes = [d, C.c_int, ip, u32p, C.POINTER(u32p), C.POINTER(C.POINTER(C.c_uint16)), vp, dp, vp,
+                          C.c_int, C.c_int]
+    for name in ("gsl_rng_gaussian_ziggurat", "gsl_rng_gamma", "digammaRN", "MLdigamma", "MLtrigamma", "digammaInv"):
+        f = getattr(L, name)
+        f.restype, f.argtypes = d, [d]
+    L.gsl_rng_beta.restype, L.gsl_rng_beta.argtypes = d, [d, d]
+    L.stb_rng48_state.restype, L.stb_rng48_state.argtypes = C.c_uint64, [C.c_long]
+    L.stb_rng48_drand.restype, L.stb_rng48_drand.argtypes = d, [u64p]
+    L.stb_rng48_lrand48.restype, L.stb_rng48_lrand48.argtypes = C.c_long, [u64p]
+    L.stb_rng48_gaussian.restype, L.stb_rng48_gaussian.argtypes = d, [u64p, d]
+    L.stb_rng48_gamma.restype, L.stb_rng48_gamma.argtypes = d, [u64p, d]
+    L.stb_rng48_beta.restype, L.stb_rng48_beta.argtypes = d, [u64p, d, d]
+    L.stb_samplea_batch.restype = C.c_int
+    L.stb_samplea_batch.argtypes = [dp, C.c_size_t, C.c_int, ip, u32p, C.POINTER(u32p),
+                                    C.POINTER(C.POINTER(C.c_uint16)), dp, C.c_int, u64p, C.c_int, vp]
+    L.stb_sampleb_batch.restype = C.c_int
+    L.stb_sampleb_batch.argtypes = [dp, C.c_size_t, C.c_int, d, d, u32p, u32p, dp, u64p, C.c_int, vp]
     L.stb_last_fill_ms.restype, L.stb_last_fill_ms.argtypes = d, [vp]
     L.stb_device_table.restype, L.stb_device_table.argtypes = vp, [vp, C.c_int, C.POINTER(C.c_size_t)]
     L.stb_device_count.restype, L.stb_device_count.argtypes = C.c_int, []
@@ -195,3 +218,74 @@ class Sweep:
             self.free()
         except Exception:
             pass
+
+
+class SampleStats(C.Structure):
+    """stb_sample_stats of include/psample.h."""
+
+    _fields_ = [("evals", C.c_uint64), ("rounds", C.c_uint64), ("eval_ms", C.c_double),
+                ("trace_x", C.POINTER(C.c_double)), ("trace_v", C.POINTER(C.c_double)),
+                ("trace_n", C.POINTER(C.c_uint32)), ("trace_cap", C.c_uint32)]
+
+
+class Counts:
+    """Ragged count arrays n[i][k] (uint32), t[i][k] (uint16) laid out the way samplea takes them."""
+
+    def __init__(self, n_rows, t_rows):
+        self.I = len(n_rows)
+        self.n_rows = [np.ascontiguousarray(r, dtype=np.uint32) for r in n_rows]
+        self.t_rows = [np.ascontiguousarray(r, dtype=np.uint16) for r in t_rows]
+        self.K = np.array([len(r) for r in self.n_rows], dtype=np.int32)
+        self.T = np.array([int(r.sum()) for r in self.t_rows], dtype=np.uint32)
+        self.N = np.array([int(r.sum()) for r in self.n_rows], dtype=np.uint32)
+        u32p, u16p = C.POINTER(C.c_uint32), C.POINTER(C.c_uint16)
+        self.n_pp = (u32p * self.I)(*[r.ctypes.data_as(u32p) for r in self.n_rows])
+        self.t_pp = (u16p * self.I)(*[r.ctypes.data_as(u16p) for r in self.t_rows])
+
+    def args(self):
+        ip, u32p = C.POINTER(C.c_int), C.POINTER(C.c_uint32)
+        return self.I, self.K.ctypes.data_as(ip), self.T.ctypes.data_as(u32p), self.n_pp, self.t_pp
+
+
+def _stats(C_chains, trace_cap):
+    st = SampleStats()
+    keep = None
+    if trace_cap:
+        tx = np.zeros((C_chains, trace_cap))
+        tv = np.zeros((C_chains, trace_cap))
+        tn = np.zeros(C_chains, dtype=np.uint32)
+        st.trace_x, st.trace_v = tx.ctypes.data_as(C.POINTER(C.c_double)), tv.ctypes.data_as(C.POINTER(C.c_double))
+        st.trace_n, st.trace_cap = tn.ctypes.data_as(C.POINTER(C.c_uint32)), trace_cap
+        keep = (tx, tv, tn)
+    return st, keep
+
+
+def samplea_batch(a, counts, bpar, rng, loops=1, bpar_per_chain=False, trace_cap=0):
+    """stb_samplea_batch: returns (a_new, rng_new, stats dict)."""
+    L = lib()
+    a = np.array(a, dtype=np.float64)
+    rng = np.array(rng, dtype=np.uint64)
+    bpar = np.ascontiguousarray(bpar, dtype=np.float64)
+    st, keep = _stats(a.shape[0], trace_cap)
+    dp, u64p = C.POINTER(C.c_double), C.POINTER(C.c_uint64)
+    rc = L.stb_samplea_batch(a.ctypes.data_as(dp), a.shape[0], *counts.args(), bpar.ctypes.data_as(dp),
+                             int(bpar_per_chain), rng.ctypes.data_as(u64p), loops, C.byref(st))
+    if rc:
+        raise RuntimeError(f"stb_samplea_batch failed ({rc}): " + L.stb_last_error().decode())
+    return a, rng, {"evals": st.evals, "rounds": st.rounds, "eval_ms": st.eval_ms, "trace": keep}
+
+
+def sampleb_batch(b, counts, shape, scale, apar, rng, loops=1, trace_cap=0):
+    """stb_sampleb_batch: returns (b_new, rng_new, stats dict)."""
+    L = lib()
+    b = np.array(b, dtype=np.float64)
+    rng = np.array(rng, dtype=np.uint64)
+    apar = np.ascontiguousarray(apar, dtype=np.float64)
+    st, keep = _stats(b.shape[0], trace_cap)
+    dp, u64p, u32p = C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
+    rc = L.stb_sampleb_batch(b.ctypes.data_as(dp), b.shape[0], counts.I, shape, scale, counts.N.ctypes.data_as(u32p),
+                             counts.T.ctypes.data_as(u32p), apar.ctypes.data_as(dp), rng.ctypes.data_as(u64p), loops,
+                             C.byref(st))
+    if rc:
+        raise RuntimeError(f"stb_sampleb_batch failed ({rc}): " + L.stb_last_error().decode())
+    return b, rng, {"evals": st.evals, "rounds": st.rounds, "eval_ms": st.eval_ms, "trace": keep}

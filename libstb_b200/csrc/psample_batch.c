@@ -1,0 +1,454 @@
+/*
+ * psample_batch.c -- batched samplers: C independent chains advance in lock-step, every
+ * log-posterior evaluation of a round is one batched device evaluation.
+ *
+ * Each chain replays exactly the control flow of the scalar sampler (SliceSimple,
+ * lib/sslice.c:33-80; samplea lib/samplea.c:155-225; sampleb lib/sampleb.c:79-159) on its OWN
+ * 48-bit random stream, so chain c started from stb_rng48_state(seed) makes the draws the
+ * reference makes after srand48(seed) -- up to the tiny differences of the evaluated densities
+ * (device lgamma / tree sums vs libm / sequential sums), which only matter if they flip an
+ * accept/reject comparison.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "psample.h"
+#include "rng48.h"
+#include "specfun.h"
+#include "stb_b200.h"
+#include "stb_cuda.h"
+
+uint64_t stb_rng48_state(long seed) {
+  stb_rng48 r;
+  stb_rng48_seed(&r, seed);
+  return r.x;
+}
+double stb_rng48_drand(uint64_t *state) {
+  stb_rng48 r;
+  double v;
+  r.x = *state;
+  v = stb_rng48_unit(&r);
+  *state = r.x;
+  return v;
+}
+long stb_rng48_lrand48(uint64_t *state) {
+  stb_rng48 r;
+  long v;
+  r.x = *state;
+  v = stb_rng48_lrand(&r);
+  *state = r.x;
+  return v;
+}
+extern const stb_zig_tables *stb_zig_tables_get(void);
+double stb_rng48_gaussian(uint64_t *state, double sigma) {
+  stb_rng48 r;
+  double v;
+  r.x = *state;
+  v = stb_gauss_zig(&r, stb_zig_tables_get(), sigma);
+  *state = r.x;
+  return v;
+}
+double stb_rng48_gamma(uint64_t *state, double a) {
+  stb_rng48 r;
+  double v;
+  r.x = *state;
+  v = stb_gamma(&r, stb_zig_tables_get(), a);
+  *state = r.x;
+  return v;
+}
+double stb_rng48_beta(uint64_t *state, double a, double b) {
+  stb_rng48 r;
+  double v;
+  r.x = *state;
+  v = stb_beta(&r, stb_zig_tables_get(), a, b);
+  *state = r.x;
+  return v;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* lock-step slice sampler                                                                     */
+/* ------------------------------------------------------------------------------------------ */
+typedef int (*eval_fn)(void *ctx, const double *x, const int *chain, size_t cnt, double *out);
+
+#define TOOMANY 200
+enum { PH_NEED_Y = 0, PH_TRY = 1, PH_DONE = 2 };
+
+static void trace_add(stb_sample_stats *st, size_t c, double x, double v) {
+  if (!st || !st->trace_x || !st->trace_n) return;
+  if (st->trace_n[c] < st->trace_cap) {
+    st->trace_x[c * st->trace_cap + st->trace_n[c]] = x;
+    if (st->trace_v) st->trace_v[c * st->trace_cap + st->trace_n[c]] = v;
+  }
+  st->trace_n[c]++;
+}
+
+/* xp[c]: start and result; lo[c], hi[c]: bounds.  Returns 0, or 1 + index of the first failing chain */
+static int slice_lockstep(double *xp, size_t C, const double *lo, const double *hi, uint64_t *rng, int loops,
+                          eval_fn eval, void *ctx, stb_sample_stats *st) {
+  int *phase = (int *)malloc(sizeof(int) * C), *left = (int *)malloc(sizeof(int) * C);
+  int *tries = (int *)malloc(sizeof(int) * C), *chain = (int *)malloc(sizeof(int) * C);
+  double *y = (double *)malloc(sizeof(double) * C), *r0 = (double *)malloc(sizeof(double) * C);
+  double *r1 = (double *)malloc(sizeof(double) * C), *xq = (double *)malloc(sizeof(double) * C);
+  double *val = (double *)malloc(sizeof(double) * C);
+  size_t c, cnt;
+  int rc = 0;
+  if (!phase || !left || !tries || !chain || !y || !r0 || !r1 || !xq || !val) {
+    rc = -1;
+    goto done;
+  }
+  for (c = 0; c < C; c++) {
+    if (xp[c] < lo[c] || xp[c] > hi[c]) {
+      fprintf(stderr, "SliceSimple: input value %lf outside bounds [%lg,%lg] (chain %zu)\n", xp[c], lo[c], hi[c], c);
+      rc = 1 + (int)c;
+      goto done;
+    }
+    phase[c] = loops > 0 ? PH_NEED_Y : PH_DONE;
+    left[c] = loops;
+    tries[c] = 0;
+  }
+  for (;;) {
+    /* the points this round evaluates */
+    cnt = 0;
+    for (c = 0; c < C; c++) {
+      stb_rng48 r;
+      if (phase[c] == PH_DONE) continue;
+      if (phase[c] == PH_NEED_Y)
+        xq[cnt] = xp[c];
+      else {
+        r.x = rng[c];
+        xq[cnt] = r0[c] + stb_rng48_unit(&r) * (r1[c] - r0[c]);
+        rng[c] = r.x;
+      }
+      chain[cnt++] = (int)c;
+    }
+    if (!cnt) break;
+    if (eval(ctx, xq, chain, cnt, val)) {
+      rc = -2;
+      goto done;
+    }
+    if (st) {
+      st->evals += cnt;
+      st->rounds++;
+    }
+    for (size_t j = 0; j < cnt; j++) {
+      stb_rng48 r;
+      c = (size_t)chain[j];
+      trace_add(st, c, xq[j], val[j]);
+      if (phase[c] == PH_NEED_Y) {
+        r.x = rng[c];
+        y[c] = val[j] + log(stb_rng48_unit(&r));
+        rng[c] = r.x;
+        r0[c] = lo[c];
+        r1[c] = hi[c];
+        tries[c] = 1;
+        phase[c] = PH_TRY;
+      } else {
+        if (val[j] > y[c]) {
+          xp[c] = xq[j];
+          left[c]--;
+          phase[c] = left[c] > 0 ? PH_NEED_Y : PH_DONE;
+        } else {
+          if (xq[j] < xp[c])
+            r0[c] = xq[j];
+          else
+            r1[c] = xq[j];
+          if (++tries[c] >= TOOMANY) {
+            fprintf(stderr, "SliceSimple: giving up after %d tries, range=[%lg,%lg] (chain %zu)\n", TOOMANY, r0[c],
+                    r1[c], c);
+            rc = 1 + (int)c;
+            goto done;
+          }
+        }
+      }
+    }
+  }
+done:
+  free(phase);
+  free(left);
+  free(tries);
+  free(chain);
+  free(y);
+  free(r0);
+  free(r1);
+  free(xq);
+  free(val);
+  return rc;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* samplea, batched                                                                            */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+  stb_sweep_t *sweep;
+  stb_pstat_dev_t *ps;
+  int bpar_per_chain;
+  double *ssum, *lg;
+  stb_sample_stats *st;
+} ABatch;
+
+static int aterms_batch(void *ctx, const double *x, const int *chain, size_t cnt, double *out) {
+  ABatch *ab = (ABatch *)ctx;
+  float ms = 0.f;
+  size_t j;
+  for (j = 0; j < cnt; j++)
+    if (x[j] <= 0) {
+      fprintf(stderr, "Illegal discount value in aterms()\n");
+      return 1;
+    }
+  if (stb_sweep_run(ab->sweep, x, cnt, NULL, ab->ssum, NULL)) return 1;
+  if (ab->st) ab->st->eval_ms += stb_sweep_last_fill_ms(ab->sweep);
+  if (stb_cuda_pstat_aterms_lg(ab->ps, x, chain, cnt, ab->bpar_per_chain, ab->lg, &ms)) return 1;
+  if (ab->st) ab->st->eval_ms += ms;
+  for (j = 0; j < cnt; j++) out[j] = ab->lg[j] + ab->ssum[j];
+  return 0;
+}
+
+int stb_samplea_batch(double *a, size_t C, int I, const int *K, const scnt_int *T, scnt_int **n, stcnt_int **t,
+                      const double *bpar, int bpar_per_chain, uint64_t *rng, int loops, stb_sample_stats *st) {
+  double *lo = NULL, *hi = NULL;
+  uint32_t *nn = NULL, *tt = NULL;
+  size_t total = 0, cnt = 0, c;
+  int i, k, maxn = 1, maxt = 1, rc = -1;
+  ABatch ab;
+  memset(&ab, 0, sizeof ab);
+  if (!C) return 0;
+  for (i = 0; i < I; i++) total += (size_t)K[i];
+  lo = (double *)malloc(sizeof(double) * C);
+  hi = (double *)malloc(sizeof(double) * C);
+  nn = (uint32_t *)malloc(sizeof(uint32_t) * (total ? total : 1));
+  tt = (uint32_t *)malloc(sizeof(uint32_t) * (total ? total : 1));
+  ab.ssum = (double *)malloc(sizeof(double) * C);
+  ab.lg = (double *)malloc(sizeof(double) * C);
+  if (!lo || !hi || !nn || !tt || !ab.ssum || !ab.lg) goto done;
+  /* bounds per chain, lib/samplea.c:161-177 and :217 */
+  for (c = 0; c < C; c++) {
+    double mid = a[c];
+    if (fabs(mid - A_MAX) / A_MAX < 0.00001) mid = A_MAX * 0.999 + A_MIN * 0.001;
+    if (fabs(mid - A_MIN) / A_MIN < 0.00001) mid = A_MIN * 0.999 + A_MAX * 0.001;
+    lo[c] = (mid - SQUEEZEA > A_MIN) ? mid - SQUEEZEA : A_MIN;
+    hi[c] = A_MAX;
+  }
+  /* the statistics with n > 1 in (i,k) order; table extent as lib/samplea.c:186-208 */
+  for (i = 0; i < I; i++)
+    for (k = 0; k < K[i]; k++) {
+      if ((int)t[i][k] >= maxt) maxt = t[i][k] + 1;
+      if ((int)n[i][k] >= maxn) maxn = n[i][k] + 1;
+      if (n[i][k] > 1) {
+        nn[cnt] = n[i][k];
+        tt[cnt] = t[i][k];
+        cnt++;
+      }
+    }
+  {
+    /* the same clamps S_make applies (lib/stable.c:118-129) */
+    unsigned Mx = maxt < 10 ? 10u : (unsigned)maxt, Nx = (unsigned)maxn < Mx ? Mx : (unsigned)maxn;
+    ab.sweep = stb_sweep_create(Nx, Mx, 0);
+  }
+  if (!ab.sweep || stb_sweep_set_pairs(ab.sweep, nn, tt, cnt)) goto done;
+  ab.ps = stb_cuda_pstat_create(I, T, NULL, bpar, bpar_per_chain ? C * (size_t)I : (size_t)I, C);
+  if (!ab.ps) goto done;
+  ab.bpar_per_chain = bpar_per_chain;
+  ab.st = st;
+  rc = slice_lockstep(a, C, lo, hi, rng, loops, aterms_batch, &ab, st);
+done:
+  if (ab.sweep) stb_sweep_free(ab.sweep);
+  if (ab.ps) stb_cuda_pstat_destroy(ab.ps);
+  free(lo);
+  free(hi);
+  free(nn);
+  free(tt);
+  free(ab.ssum);
+  free(ab.lg);
+  return rc;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* sampleb, batched                                                                            */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+  stb_pstat_dev_t *ps;
+  const double *Q, *apar;
+  double shape;
+  double *qv, *av;
+  stb_sample_stats *st;
+} BBatch;
+
+static int bterms_batch(void *ctx, const double *x, const int *chain, size_t cnt, double *out) {
+  BBatch *bb = (BBatch *)ctx;
+  float ms = 0.f;
+  size_t j;
+  for (j = 0; j < cnt; j++) {
+    bb->qv[j] = bb->Q[chain[j]];
+    bb->av[j] = bb->apar[chain[j]];
+  }
+  if (stb_cuda_pstat_bterms(bb->ps, x, bb->qv, bb->av, bb->shape, cnt, 0, out, &ms)) return 1;
+  if (bb->st) bb->st->eval_ms += ms;
+  return 0;
+}
+
+#define B_ERROR 1.0e-4
+#define B_LOOPS 5
+
+int stb_sampleb_batch(double *b, size_t C, int I, double shape, double scale, const scnt_int *N, const scnt_int *T,
+                      const double *apar, uint64_t *rng, int loops, stb_sample_stats *st) {
+  double *Q = NULL, *lo = NULL, *hi = NULL, *x = NULL, *xprime = NULL, *dsum = NULL, *xs = NULL, *as = NULL;
+  int *idx = NULL, *bl = NULL;
+  size_t c, cnt;
+  int rc = -1, i;
+  float ms = 0.f;
+  double Tsum0 = shape;
+  BBatch bb;
+  memset(&bb, 0, sizeof bb);
+  if (!C) return 0;
+  if (scale <= 0) {
+    fprintf(stderr, "Illegal scale in sampleb()\n");
+    return -1;
+  }
+  Q = (double *)malloc(sizeof(double) * C);
+  lo = (double *)malloc(sizeof(double) * C);
+  hi = (double *)malloc(sizeof(double) * C);
+  x = (double *)malloc(sizeof(double) * C);
+  xprime = (double *)malloc(sizeof(double) * C);
+  dsum = (double *)malloc(sizeof(double) * C);
+  xs = (double *)malloc(sizeof(double) * C);
+  as = (double *)malloc(sizeof(double) * C);
+  idx = (int *)malloc(sizeof(int) * C);
+  bl = (int *)malloc(sizeof(int) * C);
+  bb.qv = (double *)malloc(sizeof(double) * C);
+  bb.av = (double *)malloc(sizeof(double) * C);
+  if (!Q || !lo || !hi || !x || !xprime || !dsum || !xs || !as || !idx || !bl || !bb.qv || !bb.av) goto done;
+  bb.ps = stb_cuda_pstat_create(I, T, N, NULL, 0, C);
+  if (!bb.ps) goto done;
+  /* auxiliary variables: Q_c = 1/scale - sum_i log q_i, q_i ~ Beta(b_c, N_i)  (lib/sampleb.c:90-100) */
+  if (stb_cuda_pstat_betaQ(bb.ps, b, rng, C, scale, Q, &ms)) goto done;
+  if (st) st->eval_ms += ms;
+  for (c = 0; c < C; c++)
+    if (!(Q[c] == Q[c])) {
+      fprintf(stderr, "Illegal q in sampleb(b=%lf)\n", b[c]);
+      rc = 1 + (int)c;
+      goto done;
+    }
+  for (i = 0; i < I; i++) Tsum0 += T[i];
+  /* a == 0 chains: closed-form gamma draw (lib/sampleb.c:101-118), on the host from the chain's stream */
+  for (c = 0; c < C; c++) {
+    if (apar[c] == 0) {
+      double myb;
+      if (Tsum0 > 400) {
+        do {
+          myb = Tsum0 + stb_rng48_gaussian(&rng[c], 1) * sqrt(Tsum0);
+        } while (myb <= 0);
+      } else
+        myb = stb_rng48_gamma(&rng[c], Tsum0);
+      myb /= Q[c];
+      if (myb < B_MIN) myb = B_MIN;
+      if (myb > B_MAX) myb = B_MAX;
+      b[c] = myb;
+    }
+  }
+  /* a > 0 chains: bmax warm-up in lock-step (lib/sampleb.c:51-68), then the slice sampler */
+  for (c = 0; c < C; c++) {
+    bl[c] = B_LOOPS;
+    if (apar[c] != 0) {
+      if (b[c] <= 0) {
+        fprintf(stderr, "Illegal concentration value in bmax()\n");
+        rc = 1 + (int)c;
+        goto done;
+      }
+      xprime[c] = b[c];
+      x[c] = b[c] * 1.1;
+    }
+  }
+  for (;;) {
+    cnt = 0;
+    for (c = 0; c < C; c++) {
+      if (apar[c] == 0 || bl[c] <= 0) continue;
+      if (fabs((x[c] - xprime[c]) / x[c]) > B_ERROR && --bl[c] > 0) {
+        xs[cnt] = x[c];
+        as[cnt] = apar[c];
+        idx[cnt++] = (int)c;
+      } else
+        bl[c] = 0;
+    }
+    if (!cnt) break;
+    if (stb_cuda_pstat_bterms(bb.ps, xs, NULL, as, shape, cnt, 1, dsum, &ms)) goto done;
+    if (st) {
+      st->eval_ms += ms;
+      st->rounds++;
+    }
+    for (size_t j = 0; j < cnt; j++) {
+      double val;
+      c = (size_t)idx[j];
+      val = (shape - 1) * apar[c] / x[c] - Q[c] * apar[c] + dsum[j];
+      x[c] = xprime[c];
+      xprime[c] = apar[c] * stb_digamma_inv(val / I);
+    }
+  }
+  /* slice sampler over [B_MIN, B_MAX] from the warm start, only the a > 0 chains */
+  cnt = 0;
+  for (c = 0; c < C; c++)
+    if (apar[c] != 0) {
+      xs[cnt] = xprime[c];
+      lo[cnt] = B_MIN;
+      hi[cnt] = B_MAX;
+      idx[cnt++] = (int)c;
+    }
+  if (cnt) {
+    /* compact the active chains: slice_lockstep indexes chains 0..cnt-1 */
+    uint64_t *r2 = (uint64_t *)malloc(sizeof(uint64_t) * cnt);
+    double *Q2 = (double *)malloc(sizeof(double) * cnt), *a2 = (double *)malloc(sizeof(double) * cnt);
+    stb_sample_stats sub, *sp = NULL;
+    if (!r2 || !Q2 || !a2) {
+      free(r2);
+      free(Q2);
+      free(a2);
+      goto done;
+    }
+    for (size_t j = 0; j < cnt; j++) {
+      r2[j] = rng[idx[j]];
+      Q2[j] = Q[idx[j]];
+      a2[j] = apar[idx[j]];
+    }
+    bb.Q = Q2;
+    bb.apar = a2;
+    bb.shape = shape;
+    if (st) {
+      sub = *st;
+      if (cnt != C) sub.trace_x = sub.trace_v = NULL, sub.trace_n = NULL; /* traces only when every chain is active */
+      sp = &sub;
+    }
+    bb.st = sp;
+    rc = slice_lockstep(xs, cnt, lo, hi, r2, loops, bterms_batch, &bb, sp);
+    if (st) {
+      st->evals = sub.evals;
+      st->rounds = sub.rounds;
+      st->eval_ms = sub.eval_ms;
+    }
+    if (rc > 0) rc = 1 + idx[rc - 1];
+    for (size_t j = 0; j < cnt; j++) {
+      rng[idx[j]] = r2[j];
+      b[idx[j]] = xs[j];
+    }
+    free(r2);
+    free(Q2);
+    free(a2);
+  } else
+    rc = 0;
+done:
+  if (bb.ps) stb_cuda_pstat_destroy(bb.ps);
+  free(Q);
+  free(lo);
+  free(hi);
+  free(x);
+  free(xprime);
+  free(dsum);
+  free(xs);
+  free(as);
+  free(idx);
+  free(bl);
+  free(bb.qv);
+  free(bb.av);
+  return rc;
+}

@@ -62,6 +62,12 @@ extern "C" int stb_cuda_device_count(void) {
 }
 
 extern "C" const char *stb_cuda_last_error(void) { return g_err; }
+extern "C" void stb_cuda_set_error(const char *what, int code) {
+  if (code > 0)
+    snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString((cudaError_t)code));
+  else
+    snprintf(g_err, sizeof g_err, "%s", what);
+}
 
 extern "C" stb_dev_t *stb_cuda_table_create(int want_S, int want_V, int is_float) {
   if (stb_cuda_device_count() <= 0) {

@@ -101,6 +101,27 @@ int stb_cuda_sweep_run(stb_sweep_dev_t *w, const double *a, size_t na, double *g
 /* tables one launch fills side by side for this extent on this device */
 int stb_cuda_sweep_tables_in_flight(const stb_sweep_dev_t *w);
 
+/*
+ * Per-restaurant statistics on the device and the I-term reductions of the batched samplers
+ * (psample_cuda.cu).  T, N: uint32[I] (either may be NULL when unused); bpar: bpar_elems doubles,
+ * [I] shared by all chains or [C][I]; max_evals: most evaluations one call will carry.
+ */
+typedef struct stb_pstat_dev stb_pstat_dev_t;
+stb_pstat_dev_t *stb_cuda_pstat_create(int I, const uint32_t *T, const uint32_t *N, const double *bpar,
+                                       size_t bpar_elems, size_t max_evals);
+void stb_cuda_pstat_destroy(stb_pstat_dev_t *p);
+/* out[j] = sum_i [T_i log x_j + lgamma(T_i + b_i/x_j) - lgamma(b_i/x_j)], b row = chain[j] if per chain */
+int stb_cuda_pstat_aterms_lg(stb_pstat_dev_t *p, const double *x, const int *chain, size_t cnt, int bpar_per_chain,
+                             double *out, float *ms);
+/* digamma_sum==0: out[j] = -Q_j x_j + (shape-1) log x_j + sum_i [lgamma(T_i + x_j/a_j) - lgamma(x_j/a_j)];
+ * digamma_sum!=0: out[j] = sum_i digamma(T_i + x_j/a_j) */
+int stb_cuda_pstat_bterms(stb_pstat_dev_t *p, const double *x, const double *Q, const double *apar, double shape,
+                          size_t cnt, int digamma_sum, double *out, float *ms);
+/* Q[c] = 1/scale - sum_i log Beta(b_in[c], N_i) on chain c's own 48-bit stream rng[c] (in/out) */
+int stb_cuda_pstat_betaQ(stb_pstat_dev_t *p, const double *b_in, uint64_t *rng, size_t C, double scale, double *Q,
+                         float *ms);
+void stb_cuda_set_error(const char *what, int code);
+
 /* raw device pointer of a table (for the batched samplers and for tests) */
 void *stb_cuda_table_ptr(stb_dev_t *d, int which);
 
