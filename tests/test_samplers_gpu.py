@@ -1,0 +1,183 @@
+"""samplea (scalar and batched) and batched sampleb on the GPU against the compiled reference
+(slice-sampler build), chain by chain under identical 48-bit streams.
+
+Bars: every evaluated log-posterior within 1e-12 relative (abs floor 1) of the same formula
+evaluated with the REFERENCE's table and libm; draws agree to 1e-9 relative and the streams stay
+in step (same number of uniforms consumed) -- a flipped accept/reject would break both."""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import pytest
+
+import libstb_b200 as stb
+from tests import harness
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not os.path.exists(harness.REF_SLICE_SO), reason="reference build not present")]
+
+libc = C.CDLL(None)
+libc.drand48.restype = C.c_double
+libc.srand48.argtypes = [C.c_long]
+
+
+def _ref():
+    R = harness.ref(slice_build=True)
+    d, u32p = C.c_double, C.POINTER(C.c_uint32)
+    R.samplea.restype = d
+    R.samplea.argtypes = [d, C.c_int, C.POINTER(C.c_int), u32p, C.POINTER(u32p), C.POINTER(C.POINTER(C.c_uint16)),
+                          C.c_void_p, C.POINTER(d), C.c_void_p, C.c_int, C.c_int]
+    R.sampleb.restype, R.sampleb.argtypes = d, [d, C.c_int, d, d, u32p, u32p, d, C.c_void_p, C.c_int, C.c_int]
+    return R
+
+
+def _counts(seed, I, K, nmax):
+    """The C4 recipe of SURVEY.md 8d at reduced size: n = 1 + floor(u^3 nmax), t <= n^0.6."""
+    libc.srand48(seed)
+    n_rows, t_rows = [], []
+    for _ in range(I):
+        nr, tr = [], []
+        for _ in range(K):
+            n = 1 + int(libc.drand48() ** 3 * nmax)
+            t = min(n, 1 + int(libc.drand48() * n ** 0.6))
+            nr.append(n)
+            tr.append(t)
+        n_rows.append(nr)
+        t_rows.append(tr)
+    return stb.Counts(n_rows, t_rows)
+
+
+def _aterms_reference(R, cts, bpar, x):
+    """lib/samplea.c:46-83 evaluated with the reference's own table and libm's lgamma."""
+    maxn = max(int(r.max()) for r in cts.n_rows) + 1
+    maxt = max(int(r.max()) for r in cts.t_rows) + 1
+    sp = R.S_make(maxn, maxt, maxn, maxt, x, 1)
+    val = 0.0
+    for i in range(cts.I):
+        Ti = int(cts.T[i])
+        val += Ti * math.log(x) + math.lgamma(Ti + bpar[i] / x) - math.lgamma(bpar[i] / x)
+        for n, t in zip(cts.n_rows[i], cts.t_rows[i]):
+            if n > 1:
+                val += R.S_S(sp, int(n), int(t))
+    R.S_free(sp)
+    return val
+
+
+def test_scalar_samplea_matches_reference():
+    L, R = stb.lib(), _ref()
+    cts = _counts(42, I=12, K=10, nmax=400)
+    bpar = np.full(cts.I, 10.0)
+    dp = C.POINTER(C.c_double)
+    a_ref = a_our = 0.5
+    for step in range(4):
+        libc.srand48(500 + step)
+        a_ref = R.samplea(a_ref, *cts.args(), None, bpar.ctypes.data_as(dp), None, 2, 0)
+        s_ref = libc.drand48()
+        libc.srand48(500 + step)
+        a_our = L.samplea(a_our, *cts.args(), None, bpar.ctypes.data_as(dp), None, 2, 0)
+        assert libc.drand48() == s_ref, "different numbers of draws consumed"
+        assert a_our == pytest.approx(a_ref, rel=1e-9)
+        assert 0.01 <= a_our <= 0.98
+        a_our = a_ref
+
+
+def test_batched_samplea_matches_reference_chain_by_chain():
+    L, R = stb.lib(), _ref()
+    cts = _counts(7, I=10, K=12, nmax=600)
+    bpar = np.full(cts.I, 10.0)
+    Cn = 24
+    a0 = 0.05 + 0.9 * (np.arange(Cn) + 0.5) / Cn
+    seeds = 12345 + np.arange(Cn)
+    rng0 = np.array([L.stb_rng48_state(int(s)) for s in seeds], dtype=np.uint64)
+    a1, rng1, st = stb.samplea_batch(a0, cts, bpar, rng0, loops=2, trace_cap=64)
+    tx, tv, tn = st["trace"]
+    assert st["evals"] == int(tn.sum()) and st["rounds"] >= 4
+    dp = C.POINTER(C.c_double)
+    for c in range(Cn):
+        libc.srand48(int(seeds[c]))
+        a_ref = R.samplea(float(a0[c]), *cts.args(), None, bpar.ctypes.data_as(dp), None, 2, 0)
+        # stream in step: the state glibc is left in equals the chain's state
+        nxt = libc.drand48()
+        s = C.c_uint64(int(rng1[c]))
+        assert L.stb_rng48_drand(C.byref(s)) == nxt, c
+        assert a1[c] == pytest.approx(a_ref, rel=1e-9), c
+    # every evaluated log-posterior of a few chains against the reference's table + libm
+    for c in (0, Cn // 2, Cn - 1):
+        for k in range(min(int(tn[c]), 8)):
+            ref = _aterms_reference(R, cts, bpar, float(tx[c, k]))
+            assert abs(tv[c, k] - ref) <= 1e-12 * max(1.0, abs(ref)), (c, k, tv[c, k], ref)
+
+
+def test_batched_samplea_per_chain_bpar_and_errors():
+    L = stb.lib()
+    cts = _counts(3, I=6, K=8, nmax=200)
+    Cn = 5
+    bpar = np.tile(np.linspace(2.0, 30.0, Cn)[:, None], (1, cts.I))
+    rng0 = np.array([L.stb_rng48_state(100 + c) for c in range(Cn)], dtype=np.uint64)
+    a1, _, _ = stb.samplea_batch(np.full(Cn, 0.4), cts, bpar, rng0, loops=1, bpar_per_chain=True)
+    # chain c equals a one-chain run with its own bpar row
+    for c in range(Cn):
+        a_c, _, _ = stb.samplea_batch([0.4], cts, bpar[c], rng0[c:c + 1], loops=1)
+        assert a_c[0] == a1[c]
+    # start outside the slice bounds: the scalar sampler exits, the batched one names the chain
+    with pytest.raises(RuntimeError, match=r"\(3\)"):
+        stb.samplea_batch([0.5, 0.5, 0.99], cts, bpar[0], rng0[:3], loops=1)
+
+
+@pytest.mark.parametrize("I,tmax", [(40, 30), (300, 80)])
+def test_batched_sampleb_matches_reference_chain_by_chain(I, tmax):
+    L, R = stb.lib(), _ref()
+    g = np.random.default_rng(I)
+    T = g.integers(1, tmax, size=I)
+    N = T + g.integers(0, 500, size=I)
+    N[1] = 0
+    cts = stb.Counts([[int(x)] for x in N], [[int(min(x, 65535))] for x in T])
+    cts.T = T.astype(np.uint32)
+    cts.N = N.astype(np.uint32)
+    Cn = 20
+    apar = np.where(np.arange(Cn) % 5 == 0, 0.0, 0.05 + 0.9 * (np.arange(Cn) + 0.5) / Cn)
+    b0 = np.linspace(1.0, 50.0, Cn)
+    seeds = 777 + np.arange(Cn)
+    rng0 = np.array([L.stb_rng48_state(int(s)) for s in seeds], dtype=np.uint64)
+    b1, rng1, st = stb.sampleb_batch(b0, cts, 1.1, 20.0, apar, rng0, loops=2)
+    u32p = C.POINTER(C.c_uint32)
+    for c in range(Cn):
+        libc.srand48(int(seeds[c]))
+        b_ref = R.sampleb(float(b0[c]), I, 1.1, 20.0, cts.N.ctypes.data_as(u32p), cts.T.ctypes.data_as(u32p),
+                          float(apar[c]), None, 2, 0)
+        nxt = libc.drand48()
+        s = C.c_uint64(int(rng1[c]))
+        assert L.stb_rng48_drand(C.byref(s)) == nxt, c
+        assert b1[c] == pytest.approx(b_ref, rel=1e-9), (c, apar[c])
+
+
+def test_config4_recipe_small_slice():
+    """BASELINE config 4 statistics (100 000 nodes: I=1000 x K=100, n <= 5000) with a few chains: the
+    internal table is 5001 x <=167 per evaluation; results stay in bounds and chain 0 matches the
+    reference."""
+    L, R = stb.lib(), _ref()
+    libc.srand48(12345)
+    n_rows, t_rows = [], []
+    for _ in range(1000):
+        nr, tr = [], []
+        for _ in range(100):
+            n = 1 + int(libc.drand48() ** 3 * 5000)
+            t = min(n, 1 + int(libc.drand48() * n ** 0.6))
+            nr.append(n)
+            tr.append(t)
+        n_rows.append(nr)
+        t_rows.append(tr)
+    cts = stb.Counts(n_rows, t_rows)
+    bpar = np.full(cts.I, 10.0)
+    Cn = 6
+    a0 = 0.05 + 0.9 * (np.arange(Cn) + 0.5) / Cn
+    rng0 = np.array([L.stb_rng48_state(12345 + c) for c in range(Cn)], dtype=np.uint64)
+    a1, rng1, st = stb.samplea_batch(a0, cts, bpar, rng0, loops=1)
+    assert ((a1 >= 0.01) & (a1 <= 0.98)).all() and st["evals"] >= 2 * Cn
+    b1, _, _ = stb.sampleb_batch(np.full(Cn, 10.0), cts, 1.1, 20.0, a1, rng1, loops=1)
+    assert ((b1 >= 0.01) & (b1 <= 2000)).all()
+    dp = C.POINTER(C.c_double)
+    libc.srand48(12345)
+    a_ref = R.samplea(float(a0[0]), *cts.args(), None, bpar.ctypes.data_as(dp), None, 1, 0)
+    assert a1[0] == pytest.approx(a_ref, rel=1e-9)
