@@ -201,6 +201,92 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# secondary workloads of BASELINE.json (reported under "extras", outside the timed region)
+# ------------------------------------------------------------------------------------------------
+def config4_counts():
+    """SURVEY.md 8d recipe: srand48(12345); I=1000 x K=100; n = 1+floor(u^3 5000), t = min(n, 1+floor(u n^0.6))."""
+    import libstb_b200 as stb
+
+    libc = C.CDLL(None)
+    libc.drand48.restype = C.c_double
+    libc.srand48.argtypes = [C.c_long]
+    libc.srand48(12345)
+    n_rows, t_rows = [], []
+    for _ in range(1000):
+        nr, tr = [], []
+        for _ in range(100):
+            n = 1 + int(libc.drand48() ** 3 * 5000)
+            t = min(n, 1 + int(libc.drand48() * n ** 0.6))
+            nr.append(n)
+            tr.append(t)
+        n_rows.append(nr)
+        t_rows.append(tr)
+    return stb.Counts(n_rows, t_rows)
+
+
+def run_extras():
+    import numpy as np
+
+    import libstb_b200 as stb
+
+    L = stb.lib()
+    out = {}
+    # --- config 3: discount sweep, N=50 000 M=5 000, a_j = (j+0.5)/4096; a 96-discount slice of the 4096 ---
+    N3, M3, na = 50_000, 5_000, 96
+    rng = np.random.default_rng(3)
+    n = rng.integers(3, N3 + 1, size=100_000).astype(np.uint32)
+    m = np.minimum(rng.integers(2, M3 + 1, size=100_000), n - 1).astype(np.uint32)
+    w = stb.Sweep(N3, M3)
+    w.set_pairs(n, m)
+    a = (np.arange(0, 4096, 4096 // na)[:na] + 0.5) / 4096
+    w.run(a[:12], gather=False, sums=True)  # warm-up
+    t0 = time.perf_counter()
+    _, sums, _ = w.run(a, gather=False, sums=True)
+    wall = time.perf_counter() - t0
+    cells = cells_S(N3, M3) * na
+    out["config3_sweep"] = {"discounts": na, "of": 4096, "tables_per_launch": w.tables_in_flight,
+                            "cells_per_s_device": cells / (w.last_fill_ms * 1e-3), "cells_per_s_e2e": cells / wall,
+                            "hbm_frac": cells * 8 / (w.last_fill_ms * 1e-3) / 1e9 / 6544.7,
+                            "finite": bool(np.isfinite(sums).all())}
+    w.free()
+    # --- config 4: batched samplea + sampleb, 100 000 nodes, C chains, loops=1 ---
+    cts = config4_counts()
+    Cn = 1024
+    bpar = np.full(cts.I, 10.0)
+    a0 = 0.05 + 0.9 * (np.arange(Cn) + 0.5) / Cn
+    r0 = np.array([L.stb_rng48_state(12345 + c) for c in range(Cn)], dtype=np.uint64)
+    stb.samplea_batch(a0[:64], cts, bpar, r0[:64], loops=1)  # warm-up
+    t0 = time.perf_counter()
+    a1, r1, sa = stb.samplea_batch(a0, cts, bpar, r0, loops=1)
+    b1, r2, sb = stb.sampleb_batch(np.full(Cn, 10.0), cts, 1.1, 20.0, a1, r1, loops=1)
+    wall = time.perf_counter() - t0
+    res = {"chains": Cn, "nodes": int(cts.K.sum()), "samples_per_s": 2 * Cn / wall, "wall_s": wall,
+           "a_evals": int(sa["evals"]), "a_rounds": int(sa["rounds"]), "a_device_ms": sa["eval_ms"],
+           "b_evals": int(sb["evals"]), "in_bounds": bool(((a1 >= 0.01) & (a1 <= 0.98) & (b1 >= 0.01) & (b1 <= 2000)).all())}
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libstb_ref_slice.so")
+    if os.path.exists(ref_so):  # the reference's slice build on one host core, three chains of the same recipe
+        R = C.CDLL(ref_so)
+        d, u32p = C.c_double, C.POINTER(C.c_uint32)
+        R.samplea.restype = d
+        R.samplea.argtypes = [d, C.c_int, C.POINTER(C.c_int), u32p, C.POINTER(u32p), C.POINTER(C.POINTER(C.c_uint16)),
+                              C.c_void_p, C.POINTER(d), C.c_void_p, C.c_int, C.c_int]
+        R.sampleb.restype, R.sampleb.argtypes = d, [d, C.c_int, d, d, u32p, u32p, d, C.c_void_p, C.c_int, C.c_int]
+        libc = C.CDLL(None)
+        libc.srand48.argtypes = [C.c_long]
+        t0 = time.perf_counter()
+        ok = True
+        for c in range(3):
+            libc.srand48(12345 + c)
+            ar = R.samplea(float(a0[c]), *cts.args(), None, bpar.ctypes.data_as(C.POINTER(d)), None, 1, 0)
+            R.sampleb(10.0, cts.I, 1.1, 20.0, cts.N.ctypes.data_as(u32p), cts.T.ctypes.data_as(u32p), ar, None, 1, 0)
+            ok = ok and abs(ar - a1[c]) <= 1e-9 * abs(ar)
+        res["cpu_reference"] = {"samples_per_s": 6 / (time.perf_counter() - t0), "cores": 1, "chains": 3,
+                                "a_draws_match": bool(ok)}
+    out["config4_samplers"] = res
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # this repo's arm
 # ------------------------------------------------------------------------------------------------
 def run_own(args):
@@ -328,6 +414,11 @@ def run_own(args):
         if cpu:
             line["cpu_baseline"] = cpu
     t.free()
+    if rank == 0 and world == 1 and not args.no_extras and (N, M) == (N_ROWS, M_COLS):
+        try:
+            line["extras"] = run_extras()
+        except Exception as exc:  # the extras never take the headline line down
+            line["extras"] = {"error": repr(exc)}
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -348,6 +439,7 @@ def main():
     ap.add_argument("--rows", type=int, default=N_ROWS, help="development only; the judged run uses the default")
     ap.add_argument("--cols", type=int, default=M_COLS, help="development only; the judged run uses the default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config 3 / config 4 side measurements")
     ap.add_argument("--allow-short-warmup", action="store_true", help="profiling runs only")
     args = ap.parse_args()
     if args.impl == "reference":
