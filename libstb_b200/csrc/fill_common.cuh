@@ -82,6 +82,26 @@ __device__ __forceinline__ double div_pos(double x, double d) {
   return fma(fma(-d, q, x), r, q);
 }
 
+/*
+ * Same value with the exponent as an integer: kbias = E + 0x80000000 - 1023 (mod 2^32), so that
+ * (hi >> 20) + kbias is the low word of the double 2^52 + 2^31 + (E + k) and one subtraction of
+ * the constant gives E + k exactly (|E + k| < 2^31).
+ */
+__device__ __forceinline__ double log_scaled_i(double x, unsigned kbias, const LogTabEntry *tab) {
+  const int hi = __double2hiint(x), lo = __double2loint(x);
+  const int frac = hi & 0xFFFFF;
+  const int idx = (frac + 0x800) >> 12;
+  const double mant = __hiloint2double(frac | 0x3FF00000, lo);
+  const double2 tb = *reinterpret_cast<const double2 *>(tab + idx);
+  const double r = fma(mant, tb.x, -1.0);
+  double t = fma(r, 0.2, -0.25);
+  t = fma(r, t, 1.0 / 3.0);
+  t = fma(r, t, -0.5);
+  const double p = fma(r * r, t, r);
+  const double Ek = __hiloint2double(0x43300000, (int)(((unsigned)hi >> 20) + kbias)) - LOG_EBIAS;
+  return fma(Ek, 0.693147180559945309417232, tb.y + p);
+}
+
 template <typename OutT>
 __device__ __forceinline__ void st_out(OutT *p, double v) {
   *p = (OutT)v;

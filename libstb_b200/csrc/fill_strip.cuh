@@ -98,7 +98,7 @@ struct StripCfg {
   static constexpr int ROW_BYTES = (CP + (HAS_V ? 32 : 0)) * 8;
   // consumer batch slots per strip: as many as fit beside the other shared-memory users, an
   // even number (a producer batch is two of them), at most 16
-  static constexpr int FIXED = 4352 + (G + 1) * (ST_NBR * ST_B * 8 + ST_NBR * 4 + 16) + G * (ST_NJ * 32 * 8 + 512);
+  static constexpr int FIXED = 4352 + (G + 1) * (ST_NBR * ST_B * 8 + ST_NBR * 4 + 16) + G * (ST_NJ * 32 * 4 + 512);
   static constexpr int NB_FIT = ((227 * 1024 - FIXED) / G / ROW_BYTES / ST_RB - 1) & ~1;
   static constexpr int NB = NB_FIT > 16 ? 16 : NB_FIT;
   static constexpr int RS = NB * ST_RB;  // ring rows; rows RS..RS+7 duplicate rows 0..7
@@ -123,7 +123,8 @@ struct alignas(16) StripSub {  // per strip
   // steps never wrap.
   double xring[(Cfg::RS + ST_RB) * Cfg::CP];
   double yring[HAS_V ? (Cfg::RS + ST_RB) * 32 : 2];
-  double ering[ST_NJ * 32];  // (double)E - LOG_EBIAS per (producer batch, lane)
+  unsigned ering[ST_NJ * 32];  // E + 0x80000000 - 1023 (mod 2^32) per (producer batch, lane): log_scaled_i
+  int pad0[2];
   unsigned long long full[Cfg::NB];
   int empty_gen[Cfg::NB];  // slot s was last released by consumer batch q = s + (gen-1)*NB
   int next_q;
@@ -396,7 +397,7 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
       yin *= sc;
       E += e;
       elow = (int)E;
-      sb.ering[(p & (ST_NJ - 1)) * 32 + lane] = (double)E - LOG_EBIAS;
+      sb.ering[(p & (ST_NJ - 1)) * 32 + lane] = (unsigned)elow + (0x80000000u - 1023u);
     }
     // scale that brings the left neighbour's values into this lane's units, fixed for the batch
     const int bs = jb & (ST_NBR - 1), os = p & (ST_NBR - 1);
@@ -473,8 +474,8 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
     d[6] = g.nbatch;
     unsigned long long gt_end;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_end));
-    d[7] = (long long)gt_end;
-    d[5] = (long long)gt_start;
+    d[7] = (long long)(gt_end - gt_start);
+    d[5] = dbgacc[5];
   }
 #endif
   // a partial last row batch never sees its eighth row: release it now that every row exists
@@ -494,6 +495,7 @@ __device__ void strip_consumer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
   OutT *tabS = (OutT *)tb.tabS;
   OutT *tabV = (OutT *)tb.tabV;
   const bool first_strip = (g.rs == 0);
+  const unsigned ld32 = (unsigned)P.ld;  // 8 rows x ld elements stay far below 2^32
 
   for (;;) {
     int q = 0;
@@ -526,15 +528,15 @@ __device__ void strip_consumer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
 #pragma unroll
         for (int i = 0; i < ST_RB; i++) xv[i] = xc[i * CP];
         if (HAS_S) {
-          const double Ea = sb.ering[(j0 & (ST_NJ - 1)) * 32 + pl];
-          const double Eb = sb.ering[((j0 + 1) & (ST_NJ - 1)) * 32 + pl];
+          const unsigned Ea = sb.ering[(j0 & (ST_NJ - 1)) * 32 + pl];
+          const unsigned Eb = sb.ering[((j0 + 1) & (ST_NJ - 1)) * 32 + pl];
           double v[ST_RB];
 #pragma unroll
-          for (int i = 0; i < ST_RB; i++) v[i] = log_scaled(xv[i], (i >= thr) ? Eb : Ea, logtab);
+          for (int i = 0; i < ST_RB; i++) v[i] = log_scaled_i(xv[i], (i >= thr) ? Eb : Ea, logtab);
           if (lane_ok) {
             OutT *pS = tabS + cell0;
 #pragma unroll
-            for (int i = 0; i < ST_RB; i++) st_out(pS + (size_t)i * P.ld, v[i]);
+            for (int i = 0; i < ST_RB; i++) st_out(pS + (size_t)((unsigned)i * ld32), v[i]);
             if (first_strip && col == 0) {
 #pragma unroll
               for (int i = 0; i < ST_RB; i++) tb.s1[r0 + i] = v[i];
@@ -548,7 +550,7 @@ __device__ void strip_consumer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
           if (lane_ok && !(first_strip && col == 0)) {
             OutT *pV = tabV + cell0;
 #pragma unroll
-            for (int i = 0; i < ST_RB; i++) st_out(pV + (size_t)i * P.ld, div_pos(xv[i], den[i]));
+            for (int i = 0; i < ST_RB; i++) st_out(pV + (size_t)((unsigned)i * ld32), div_pos(xv[i], den[i]));
           }
         }
       } else if (lane_ok) {
@@ -560,7 +562,7 @@ __device__ void strip_consumer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
           const size_t off = cell0 + (size_t)i * P.ld;
           if (HAS_S) {
             const int j = (toff + i) >> ST_SH;
-            const double v = log_scaled(xv, sb.ering[(j & (ST_NJ - 1)) * 32 + pl], logtab);
+            const double v = log_scaled_i(xv, sb.ering[(j & (ST_NJ - 1)) * 32 + pl], logtab);
             st_out(tabS + off, v);
             if (first_strip && col == 0) tb.s1[r] = v;
           }
@@ -889,7 +891,8 @@ struct StripFillArgs {
  */
 inline int strip_fill(StripState *st, const StripFillArgs &A, cudaStream_t stream, cudaEvent_t ev_end, char *err,
                       size_t errlen) {
-  if (A.N >= 0x7ff00000u || A.M > A.N || A.M < 1) {
+  // the per-lane exponent is carried in 32 bits: N log2 N must stay below 2^31
+  if (A.N > 50000000u || A.M > A.N || A.M < 1 || (unsigned long long)A.ld * 8 >= 0xffffffffull) {
     snprintf(err, errlen, "strip_fill: unsupported extent N=%u M=%u", A.N, A.M);
     return -1;
   }
@@ -963,7 +966,6 @@ inline int strip_fill(StripState *st, const StripFillArgs &A, cudaStream_t strea
         static long long h[1024 * 8];
         cudaMemcpy(h, st->dbg, sizeof h, cudaMemcpyDeviceToHost);
         const int show[6] = {0, 1, 2, nctas / 2, nctas - 2, nctas - 1};
-        const long long t00 = h[5];
         for (int si = 0; si < 6; si++) {
           const int c = show[si];
           if (c < 0 || c >= nctas || (si && c <= show[si - 1])) continue;
@@ -973,8 +975,8 @@ inline int strip_fill(StripState *st, const StripFillArgs &A, cudaStream_t strea
             if (nb <= 0 || (size_t)c * pl.G + gi >= 1024) continue;
             fprintf(stderr,
                     "cta %3d producer %d batches %6.0f cycles/batch: slot-wait %.0f in-wait %.0f out-wait %.0f setup %.0f "
-                    "steps %.0f | start %+.1f us end %+.1f us\n",
-                    c, gi, nb, d[0] / nb, d[1] / nb, d[2] / nb, d[3] / nb, d[4] / nb, (d[5] - t00) / 1e3, (d[7] - t00) / 1e3);
+                    "steps %.0f publish %.0f | busy %.1f us\n",
+                    c, gi, nb, d[0] / nb, d[1] / nb, d[2] / nb, d[3] / nb, d[4] / nb, d[5] / nb, d[7] / 1e3);
           }
         }
       }
