@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libstb_b200.so")
+# STB_B200_LIB: another build of the same library (development: profiling builds); never a fallback
+LIB_PATH = os.environ.get("STB_B200_LIB") or os.path.join(_HERE, "lib", "libstb_b200.so")
 
 # flag bits, include/stable.h
 S_STABLE, S_UVTABLE, S_FLOAT, S_VERBOSE, S_QUITONBOUND, S_THREADS, S_ASYMPT = 1, 2, 4, 8, 16, 32, 64

@@ -15,6 +15,26 @@
 namespace stb {
 
 constexpr int LOGTAB_N = 257;  // c_i = 1 + i/256, i = 0..256
+// In shared memory the table is kept LOGTAB_REP times, interleaved (entry i of copy j at
+// [i*8 + j]): copy j occupies only the four banks 4j..4j+3, and lane l reads copy l % 8, so the
+// eight lanes a 16-byte shared-memory load serves per pass never collide whatever their
+// mantissas are.  (One copy costs ~2.7 passes per load at random indices: measured as the largest
+// consumer of shared-memory bandwidth of the fill.)
+constexpr int LOGTAB_REP = 8;
+// The strip kernel's table holds ONLY log(c_i) (8 bytes): 1/c_i is taken from the hardware's
+// single-precision reciprocal of c_i (exactly representable, so the result is a fixed function of
+// i), widened to double with integer operations; the table is built on the device with the same
+// instruction, T[i] = -log(rcp(c_i)), which makes log(mant) = T[i] + log1p(mant*rcp(c_i) - 1) an
+// identity whatever the last bit of the reciprocal is.  Half the shared-memory traffic of the
+// 16-byte entries.  Kept LOGTAB_REP8 times (copy j in 8-byte bank j, lane l reads copy l % 16).
+constexpr int LOGTAB_REP8 = 16;
+
+__device__ __forceinline__ double logtab_inv_c(int idx) {  // rcp(1 + idx/256) as a double, idx = 0..256
+  float invf;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(invf) : "f"(__int_as_float(0x3F800000 + (idx << 15))));
+  const unsigned fb = __float_as_uint(invf);  // positive normal: widen by moving the bits
+  return __hiloint2double((int)((fb >> 3) + 0x38000000u), (int)(fb << 29));
+}
 constexpr long long FILL_WATCHDOG = 6000000000LL;  // cycles a wait may last before the fill aborts
 
 struct __align__(16) LogTabEntry {
@@ -87,12 +107,15 @@ __device__ __forceinline__ double div_pos(double x, double d) {
  * (hi >> 20) + kbias is the low word of the double 2^52 + 2^31 + (E + k) and one subtraction of
  * the constant gives E + k exactly (|E + k| < 2^31).
  */
+template <int REP = 1>
 __device__ __forceinline__ double log_scaled_i(double x, unsigned kbias, const LogTabEntry *tab) {
   const int hi = __double2hiint(x), lo = __double2loint(x);
   const int frac = hi & 0xFFFFF;
   const int idx = (frac + 0x800) >> 12;
   const double mant = __hiloint2double(frac | 0x3FF00000, lo);
-  const double2 tb = *reinterpret_cast<const double2 *>(tab + idx);
+  // REP > 1: the table is stored REP times, entry i of copy j at [i*REP + j], and tab already
+  // points at this lane's copy (see LOGTAB_REP)
+  const double2 tb = *reinterpret_cast<const double2 *>(tab + idx * REP);
   const double r = fma(mant, tb.x, -1.0);
   double t = fma(r, 0.2, -0.25);
   t = fma(r, t, 1.0 / 3.0);
@@ -100,6 +123,31 @@ __device__ __forceinline__ double log_scaled_i(double x, unsigned kbias, const L
   const double p = fma(r * r, t, r);
   const double Ek = __hiloint2double(0x43300000, (int)(((unsigned)hi >> 20) + kbias)) - LOG_EBIAS;
   return fma(Ek, 0.693147180559945309417232, tb.y + p);
+}
+
+/* the same with the 8-byte table (tab points at this lane's copy, entries REP apart) */
+template <int REP>
+__device__ __forceinline__ double log_scaled_r(double x, unsigned kbias, const double *tab) {
+  const int hi = __double2hiint(x), lo = __double2loint(x);
+  const int frac = hi & 0xFFFFF;
+  const int idx = (frac + 0x800) >> 12;
+  const double mant = __hiloint2double(frac | 0x3FF00000, lo);
+  const double log_c = tab[idx * REP];
+  const double r = fma(mant, logtab_inv_c(idx), -1.0);
+  double t = fma(r, 0.2, -0.25);
+  t = fma(r, t, 1.0 / 3.0);
+  t = fma(r, t, -0.5);
+  const double p = fma(r * r, t, r);
+  const double Ek = __hiloint2double(0x43300000, (int)(((unsigned)hi >> 20) + kbias)) - LOG_EBIAS;
+  return fma(Ek, 0.693147180559945309417232, log_c + p);
+}
+
+/* builds the 8-byte table on the device: one thread per entry */
+__global__ void logtab8_build_kernel(double *tab) {
+  const int i = threadIdx.x + blockIdx.x * blockDim.x;
+  if (i >= LOGTAB_N) return;
+  const double inv = logtab_inv_c(i);
+  tab[i] = (inv == 1.0) ? 0.0 : -log(inv);
 }
 
 template <typename OutT>

@@ -55,8 +55,11 @@ constexpr int ST_RB = 8;          // rows per consumer batch
 constexpr int ST_NBR = ST_NBR_OVERRIDE;  // boundary ring (producer batches) in shared memory
 constexpr int ST_NBG = 128;       // boundary ring (producer batches) in global memory, per CTA boundary
 constexpr int ST_NJ = 16;         // producer batches of per-lane exponents kept
-constexpr int ST_WARPS = 16;      // warps per CTA
-constexpr int ST_LOADER = 4, ST_FLUSHER = 8;  // helper warps; producers are warps 0..G-1, the rest consume
+#ifndef ST_WARPS_OVERRIDE
+#define ST_WARPS_OVERRIDE 16
+#endif
+constexpr int ST_WARPS = ST_WARPS_OVERRIDE;  // warps per CTA
+constexpr int ST_LOADER = 7, ST_FLUSHER = 11;  // helper warps (sub-partition 3, away from producer 0); producers are warps 0..G-1, the rest consume
 #ifndef ST_CONS_SLEEP
 #define ST_CONS_SLEEP 40  // ns a consumer sleeps between polls of its batch barrier
 #endif
@@ -78,7 +81,7 @@ struct StripParams {
   uint4 *gring;  // [boundaries][ST_NBG*(ST_B+1)] flag-in-data entries, zeroed before each launch
   int *gtaken;   // [boundaries] reader progress (back-pressure only)
   int *abort_flag;
-  const LogTabEntry *logtab;
+  const double *logtab;  // 8-byte table, LOGTAB_N entries (fill_common.cuh)
   int ncons;       // consumer warps per strip in use (tuning knob)
   int spread;      // consumer warps allowed on each producer's SM sub-partition (0..3)
   long long *dbg;  // STB_PROFILE_PRODUCER builds: [ctas][8] cycle counters of the producer's phases
@@ -98,7 +101,7 @@ struct StripCfg {
   static constexpr int ROW_BYTES = (CP + (HAS_V ? 32 : 0)) * 8;
   // consumer batch slots per strip: as many as fit beside the other shared-memory users, an
   // even number (a producer batch is two of them), at most 16
-  static constexpr int FIXED = 4352 + (G + 1) * (ST_NBR * ST_B * 8 + ST_NBR * 4 + 16) + G * (ST_NJ * 32 * 4 + 512);
+  static constexpr int FIXED = 256 + LOGTAB_N * LOGTAB_REP8 * 8 + (G + 1) * (ST_NBR * ST_B * 8 + ST_NBR * 4 + 16) + G * (ST_NJ * 32 * 4 + 512);
   static constexpr int NB_FIT = ((227 * 1024 - FIXED) / G / ROW_BYTES / ST_RB - 1) & ~1;
   static constexpr int NB = NB_FIT > 16 ? 16 : NB_FIT;
   static constexpr int RS = NB * ST_RB;  // ring rows; rows RS..RS+7 duplicate rows 0..7
@@ -126,14 +129,14 @@ struct alignas(16) StripSub {  // per strip
   unsigned ering[ST_NJ * 32];  // E + 0x80000000 - 1023 (mod 2^32) per (producer batch, lane): log_scaled_i
   int pad0[2];
   unsigned long long full[Cfg::NB];
-  int empty_gen[Cfg::NB];  // slot s was last released by consumer batch q = s + (gen-1)*NB
+  int empty_gen[Cfg::NB];  // units (8 rows x 32 columns) of slot s finished so far: U per tenant batch
   int next_q;
   int pad[3];
 };
 
 template <int K, int G, bool HAS_V>
 struct StripSmem {
-  LogTabEntry logtab[LOGTAB_N + 1];
+  double logtab[LOGTAB_N * LOGTAB_REP8];
   StripSub<K, G, HAS_V> sub[G];
   BRing ring[G + 1];  // ring g feeds strip g; ring 0 is filled by the loader, ring G drained by the flusher
 };
@@ -254,63 +257,136 @@ __device__ __forceinline__ int strip_qdone(int p, int phi, int L) {
 
 // ---- producer ----------------------------------------------------------------------------------------
 /*
- * NS recurrence steps.  x[k]: the lane's K columns; the coefficient of column m_k in row n is
- * (n-1) - m_k a, formed per step from nm1 = n-1 and ma[k] = m_k a exactly like that (one rounding,
- * independent of where a strip starts, so every geometry produces the same bits); yin: the left
- * neighbour's value one row up, in this lane's units; scn: the per-batch factor that brings the
- * neighbour's units to this lane's.  Everything is stored unconditionally: rows that do not exist
- * (before the strip's first row, past N) land in ring slots the consumers never read as valid.
+ * Shared-memory accesses of the recurrence by 32-bit shared address with immediate offsets
+ * (volatile: kept in program order, which is what makes a value stored by one lane in step i
+ * readable by its neighbour in step i+1 without a warp barrier -- one warp's shared-memory
+ * instructions execute in order).
  */
-template <int K, bool HAS_V, bool DUP, int CP, int RS, int NS>
-__device__ __forceinline__ void strip_steps(double (&x)[K], const double (&ma)[K], double &nm1, double &yin,
-                                            const double scn, const double *__restrict__ bnd,
-                                            const bool take_bnd, const bool write_out, double *__restrict__ xr, double *__restrict__ yr,
-                                            double *__restrict__ outp) {
-#pragma unroll
-  for (int i = 0; i < NS; i++) {
-    // the left neighbour's last column BEFORE this step's update: its value one row up from
-    // the row this lane makes in the NEXT step
-    double s = shfl_up_d(x[K - 1]);
-    if (take_bnd) s = bnd[i];
-#pragma unroll
-    for (int k = K - 1; k >= 1; k--) x[k] = fma(nm1 - ma[k], x[k], x[k - 1]);
-    x[0] = fma(nm1 - ma[0], x[0], yin);
-    yin = s * scn;
-    nm1 += 1.0;
-    if (K == 2) {
-      *reinterpret_cast<double2 *>(xr + i * CP) = make_double2(x[0], x[1]);
-      if (DUP) *reinterpret_cast<double2 *>(xr + (RS + i) * CP) = make_double2(x[0], x[1]);
-    } else {
-#pragma unroll
-      for (int k = 0; k < K; k++) {
-        xr[i * CP + k] = x[k];
-        if (DUP) xr[(RS + i) * CP + k] = x[k];
-      }
-    }
-    if (HAS_V) {
-      yr[i * 32] = yin;
-      if (DUP) yr[(RS + i) * 32] = yin;
-    }
-    if (write_out) outp[i] = x[K - 1];
-  }
+__device__ __forceinline__ void sts_f64(unsigned a, double v) {
+  asm volatile("st.volatile.shared.f64 [%0], %1;" ::"r"(a), "d"(v));
 }
-
-/* predicated single instructions: no branch, no reconvergence point in the producer's batch loop */
-__device__ __forceinline__ void mbar_arrive_if(unsigned long long *bar, bool pred) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.u32 p, %1, 0;\n\t"
-      "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(smem_u32(bar)),
-      "r"((unsigned)pred)
-      : "memory");
-}
-__device__ __forceinline__ void st_shared_if(int *p, int v, bool pred) {
+__device__ __forceinline__ void sts_f64_if(unsigned a, double v, bool pred) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.u32 p, %2, 0;\n\t"
-      "@p st.volatile.shared.s32 [%0], %1;\n\t}" ::"r"(smem_u32(p)),
+      "@p st.volatile.shared.f64 [%0], %1;\n\t}" ::"r"(a),
+      "d"(v), "r"((unsigned)pred));
+}
+__device__ __forceinline__ double lds_f64(unsigned a) {
+  double v;
+  asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int lds_s32(unsigned a) {
+  int v;
+  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int2 lds_v2s32(unsigned a) {
+  int2 v;
+  asm volatile("ld.volatile.shared.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_s32_if(unsigned a, int v, bool pred) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.u32 p, %2, 0;\n\t"
+      "@p st.volatile.shared.s32 [%0], %1;\n\t}" ::"r"(a),
       "r"(v), "r"((unsigned)pred)
       : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_if(unsigned bar, bool pred) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.u32 p, %1, 0;\n\t"
+      "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(bar),
+      "r"((unsigned)pred)
+      : "memory");
+}
+
+/*
+ * Eight recurrence steps.  x[k]: the lane's K columns; the coefficient of column m_k in row n is
+ * (n-1) - m_k a, formed per step from nm1 = n-1 and ma[k] = m_k a exactly like that (one rounding,
+ * independent of where a strip starts, so every geometry produces the same bits); yin: the left
+ * neighbour's value one row up, in this lane's units; scn: the per-batch factor that brings the
+ * neighbour's units to this lane's.
+ *
+ * The left neighbour's last column after step i-1 is what this lane needs in step i+1 (the lanes
+ * walk a diagonal).  It is read back from where the neighbour stored it for the consumers -- the
+ * x ring; lane 0 reads the boundary ring instead -- by ONE load issued at the top of step i and
+ * first used at the bottom of step i (yin for step i+1), so that its latency hides behind the
+ * step's own arithmetic: the row-to-row critical path is the DFMA, nothing else.  nb_addr is the
+ * address of the next such load and advances by nb_stride (a ring row / one boundary entry);
+ * the first step of a batch gets the value in nb0 (the batch set-up fetches it after the
+ * renormalisation).  Everything is stored unconditionally: rows that do not exist (before the
+ * strip's first row, past N) land in ring slots the consumers never read as valid.
+ */
+template <int K, bool HAS_V, bool DUP, int CP, int RS, bool FIRST>
+__device__ __forceinline__ void strip_steps(double (&x)[K], const double (&ma)[K], double &nm1, double &yin,
+                                            const double nb0, const double scn, unsigned &nb_addr,
+                                            const unsigned nb_stride, const bool write_out, const unsigned xr,
+                                            const unsigned yr, const unsigned outp) {
+#pragma unroll
+  for (int i = 0; i < ST_RB; i++) {
+    double nb = nb0;
+    if (!(FIRST && i == 0)) {
+      nb = lds_f64(nb_addr);
+      nb_addr += nb_stride;
+    }
+    // Stores (kept in program order) are placed where their operands are long since ready: columns
+    // 0..K-2 of the PREVIOUS row go out now, before this step's arithmetic; only column K-1 -- the
+    // one the right-hand neighbour reads back in its next step -- is stored in its own step, and
+    // it is the first value the step computes.  (Constant offsets fold into the instructions.)
+    if (i > 0) {
+#pragma unroll
+      for (int k = 0; k < K - 1; k++) {
+        sts_f64(xr + ((i - 1) * CP + k) * 8, x[k]);
+        if (DUP) sts_f64(xr + ((RS + i - 1) * CP + k) * 8, x[k]);
+      }
+    }
+#pragma unroll
+    for (int k = K - 1; k >= 1; k--) x[k] = fma(nm1 - ma[k], x[k], x[k - 1]);
+    x[0] = fma(nm1 - ma[0], x[0], yin);
+    nm1 += 1.0;
+    sts_f64(xr + (i * CP + K - 1) * 8, x[K - 1]);
+    if (DUP) sts_f64(xr + ((RS + i) * CP + K - 1) * 8, x[K - 1]);
+    sts_f64_if(outp + i * 8, x[K - 1], write_out);
+    yin = nb * scn;
+    if (HAS_V) {
+      sts_f64(yr + i * 32 * 8, yin);
+      if (DUP) sts_f64(yr + (RS + i) * 32 * 8, yin);
+    }
+  }
+  // the last row's remaining columns
+#pragma unroll
+  for (int k = 0; k < K - 1; k++) {
+    sts_f64(xr + ((ST_RB - 1) * CP + k) * 8, x[k]);
+    if (DUP) sts_f64(xr + ((RS + ST_RB - 1) * CP + k) * 8, x[k]);
+  }
+}
+
+/*
+ * Slow path of the producer's flow control (rare: the fast path is three register compares on
+ * words fetched half a batch earlier).  Waits until the two x-ring slots of the batch are free,
+ * the left boundary batch has arrived and the right boundary ring has room; returns false when
+ * the fill was aborted.  Not inlined: keeps the batch loop short.
+ */
+__device__ __noinline__ bool producer_wait(unsigned a_gen, int gen_need, unsigned a_written, int need_in,
+                                           unsigned a_taken, int need_out, int *abort_flag) {
+  const long long t0 = clock64();
+  unsigned spins = 0;
+  for (;;) {
+    const int2 gen = lds_v2s32(a_gen);
+    const int w = lds_s32(a_written), t = lds_s32(a_taken);
+    if (gen.x >= gen_need && gen.y >= gen_need && w >= need_in && t >= need_out) return true;
+    if ((++spins & 1023u) == 0) {
+      const int bad = ld_vol(abort_flag) || (clock64() - t0 > FILL_WATCHDOG);
+      if (__any_sync(0xffffffffu, bad)) {
+        if ((threadIdx.x & 31) == 0) atomicExch(abort_flag, 1);
+        return false;
+      }
+    }
+  }
 }
 
 template <int K, int G, bool HAS_V>
@@ -319,11 +395,10 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
                                int jlast) {
   using Cfg = StripCfg<K, G, HAS_V>;
   constexpr int CP = Cfg::CP, RS = Cfg::RS, NB = Cfg::NB;
+  constexpr int NO_NEED = -0x40000000;  // "nothing to wait for"
   const int L = P.L;
   // rin / rout always point at a ring of this CTA; without a neighbour on that side the ring is
-  // simply unused by anyone else, which keeps the step code free of branches
-  BRing *const rin_ = rin;
-  BRing *const rout_ = rout;
+  // simply unused by anyone else (and zero-filled), which keeps the step code free of branches
 
   double x[K], ma[K];
 #pragma unroll
@@ -336,16 +411,39 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
   // S^rs_rs = 1 (S^0_0 = 1 for the first strip) seeds the strip's diagonal; with phi > 0 it
   // arrives through the boundary ring like every other row
   double yin = (lane == 0 && (g.phi == 0 || !has_left)) ? 1.0 : 0.0;
+  const bool lane0 = (lane == 0);
+  const bool take_bnd = lane0 && has_left;  // lane 0 of the first strip reads zeros times zero
+  const bool write_out = has_right && (lane == L - 1);
+  // shared addresses, formed once
+  const unsigned a_xr = smem_u32(&sb.xring[lane * K]);
+  const unsigned a_yr = smem_u32(&sb.yring[HAS_V ? lane : 0]);
+  const unsigned a_er = smem_u32(&sb.ering[lane]);
+  const unsigned a_gen = smem_u32(&sb.empty_gen[0]);
+  const unsigned a_full = smem_u32(&sb.full[0]);
+  const unsigned a_in_x = smem_u32(&rin->x[0]), a_in_e = smem_u32(&rin->e[0]);
+  const unsigned a_in_written = smem_u32(&rin->written), a_in_taken = smem_u32(&rin->taken);
+  const unsigned a_out_x = smem_u32(&rout->x[0]), a_out_e = smem_u32(&rout->e[0]);
+  const unsigned a_out_written = smem_u32(&rout->written), a_out_taken = smem_u32(&rout->taken);
+  // where lane l finds its left neighbour's last column: one ring row up, one column to the left
+  const unsigned nb_stride = lane0 ? 8u : (unsigned)(CP * 8);
+
+  // exponent state: the scale of batch p+1 is fixed in the MIDDLE of batch p (any power of two is
+  // exact; sixteen + eight rows of growth stay far inside the double range), which takes the
+  // exponent extraction, the neighbour's exponent and the scale factors off the critical path
   long long E = 0;
   int elow = 0;
-  const bool lane0 = (lane == 0);
-  const bool take_bnd = lane0 && has_left;  // lane 0 of the first strip keeps its shuffled value times zero
-  const bool write_out = has_right && (lane == L - 1);
-  int qsent = -1;                                    // consumer batches released so far
-  int rows = ST_B - g.phi - (L - 1);                 // rows 0..rows-1 are complete after the current batch
-  int s0 = 0, gen_need = 0;                          // consumer slot pair of the batch, generation it must have
-  int q1slot = 0;                                    // slot of consumer batch qsent+1
-  int c_in = -1, c_out = has_right ? ld_vol(&rout->taken) : 0;
+  int e_n = 0, elow_n = 0, sE_n = 0;  // predicted for the next batch: exponent step, E, neighbour's E
+  double sc_n = 1.0;
+  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a_er), "r"(0x80000000u - 1023u));
+
+  int qsent = -1;                     // consumer batches released so far
+  int rows = ST_B - g.phi - (L - 1);  // rows 0..rows-1 are complete after the current batch
+  int cvalid_p = P.M - g.rs;
+  if (cvalid_p > P.C) cvalid_p = P.C;
+  const int U = (cvalid_p + 31) >> 5;  // units per consumer batch (see strip_consumer)
+  int s0 = 0, gen_need = 0;           // consumer slot pair of the batch, finished units it must show
+  int q1slot = 0;                     // slot of consumer batch qsent+1
+  int c_in = -1, c_out = has_right ? lds_s32(a_out_taken) : 0;
 #ifdef STB_PROFILE_PRODUCER
   long long dbgacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   unsigned long long gt_start = 0;
@@ -358,81 +456,64 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
     ST_TICK(tk0);
     // ---- flow control (uniform across the warp) ----
     // producer batch p overwrites the ring rows of consumer slots s0, s0+1 (s0 = 2p % NB); their
-    // previous tenants are consumer batches 2p-NB and 2p+1-NB, released when gen >= 2p/NB
-    if (gen_next.x < gen_need || gen_next.y < gen_need) {
-      const long long t0 = clock64();
-      unsigned spins = 0;
-      for (;;) {
-        const int2 gen = ld_vol2(&sb.empty_gen[s0]);
-        if (gen.x >= gen_need && gen.y >= gen_need) break;
-        if ((++spins & 1023u) == 0) {
-          const int bad = ld_vol(P.abort_flag) || (clock64() - t0 > FILL_WATCHDOG);
-          if (__any_sync(0xffffffffu, bad)) {
-            if (lane0) atomicExch(P.abort_flag, 1);
-            return;
-          }
-        }
-      }
-    }
-    ST_TICK(tk1);
+    // previous tenants are consumer batches 2p-NB and 2p+1-NB, released when U * (2p/NB) units
+    // of each slot are finished
     int jb = p + g.delta;
     if (jb > jlast) jb = jlast;
-    if (has_left) {
-      if (!ctr_wait<false, 0>(&rin->written, jb, P.abort_flag, c_in)) return;
+    const int need_in = has_left ? jb : NO_NEED, need_out = has_right ? p - ST_NBR : NO_NEED;
+    if (gen_next.x < gen_need || gen_next.y < gen_need || c_in < need_in || c_out < need_out) {
+      if (!producer_wait(a_gen + s0 * 4, gen_need, a_in_written, need_in, a_out_taken, need_out, P.abort_flag)) return;
+      c_in = max(c_in, need_in);
+      c_out = max(c_out, need_out);
     }
-    ST_TICK(tk1b);
-    if (has_right) {
-      if (!ctr_wait<false, 0>(&rout->taken, p - ST_NBR, P.abort_flag, c_out)) return;
-    }
-    asm volatile("" ::: "memory");
     ST_TICK(tk2);
-    // ---- renormalise ----
-    {
-      const int hi = __double2hiint(x[0]);
-      int e = ((hi >> 20) & 0x7ff) - 1023;
-      if (x[0] == 0.0) e = 0;
-      const double sc = pow2i(-e);
-#pragma unroll
-      for (int k = 0; k < K; k++) x[k] *= sc;
-      yin *= sc;
-      E += e;
-      elow = (int)E;
-      sb.ering[(p & (ST_NJ - 1)) * 32 + lane] = (unsigned)elow + (0x80000000u - 1023u);
-    }
-    // scale that brings the left neighbour's values into this lane's units, fixed for the batch
+    // ---- the batch's scale (fixed half a batch ago) ----
     const int bs = jb & (ST_NBR - 1), os = p & (ST_NBR - 1);
-    int sE = __shfl_up_sync(0xffffffffu, elow, 1);
-    if (lane0) sE = has_left ? rin_->e[bs] : elow;
-    // (lane 0 of a table's first strip has no left neighbour: its shuffled value is multiplied by 0)
+#pragma unroll
+    for (int k = 0; k < K; k++) x[k] *= sc_n;
+    yin *= sc_n;
+    E += e_n;
+    elow = elow_n;
+    int sE = sE_n;
+    if (lane0) sE = has_left ? lds_s32(a_in_e + bs * 4) : elow;
+    // (lane 0 of a table's first strip has no left neighbour: what it reads is multiplied by 0)
     const double scn = (lane0 && !has_left) ? 0.0 : pow2i(sE - elow);
-    st_shared_if(&rout_->e[os], elow, write_out);
-    const double *bnd = &rin_->x[bs * ST_B];
-    double *outp = &rout_->x[os * ST_B];
-    double *xr = &sb.xring[s0 * ST_RB * CP + lane * K];
-    double *yr = &sb.yring[HAS_V ? s0 * ST_RB * 32 + lane : 0];
+    sts_s32_if(a_out_e + os * 4, elow, write_out);
+    const unsigned bnd = a_in_x + bs * (ST_B * 8);
+    const unsigned outp = a_out_x + os * (ST_B * 8);
+    const unsigned xr = a_xr + s0 * (ST_RB * CP * 8);
+    const unsigned yr = a_yr + (HAS_V ? s0 * (ST_RB * 32 * 8) : 0);
+    // the neighbour's value for the first step, in the new units
+    double nb0 = shfl_up_d(x[K - 1]);
+    if (lane0) nb0 = lds_f64(bnd);
+    unsigned nb_addr = lane0 ? bnd + 8u : xr - 8u;
 
     ST_TICK(tk3);
     // ---- sixteen steps, eight per consumer slot; only ring rows 0..7 have duplicates ----
     if (s0 == 0)
-      strip_steps<K, HAS_V, true, CP, RS, ST_RB>(x, ma, nm1, yin, scn, bnd, take_bnd, write_out, xr, yr, outp);
+      strip_steps<K, HAS_V, true, CP, RS, true>(x, ma, nm1, yin, nb0, scn, nb_addr, nb_stride, write_out, xr, yr, outp);
     else
-      strip_steps<K, HAS_V, false, CP, RS, ST_RB>(x, ma, nm1, yin, scn, bnd, take_bnd, write_out, xr, yr, outp);
-    // mid-batch: fetch the words the NEXT batch's flow control will look at
+      strip_steps<K, HAS_V, false, CP, RS, true>(x, ma, nm1, yin, nb0, scn, nb_addr, nb_stride, write_out, xr, yr,
+                                                 outp);
+    // mid-batch: fetch the words the NEXT batch's flow control will look at, fix the next scale
     {
       int s1 = s0 + 2;
       if (s1 >= NB) s1 = 0;
-      gen_next = ld_vol2(&sb.empty_gen[s1]);
-      if (has_left) {
-        const int v = ld_vol(&rin->written);
-        c_in = v > c_in ? v : c_in;
-      }
-      if (has_right) {
-        const int v = ld_vol(&rout->taken);
-        c_out = v > c_out ? v : c_out;
-      }
+      gen_next = lds_v2s32(a_gen + s1 * 4);
+      if (has_left) c_in = max(c_in, lds_s32(a_in_written));
+      if (has_right) c_out = max(c_out, lds_s32(a_out_taken));
+      const int hi = __double2hiint(x[0]);
+      e_n = ((hi >> 20) & 0x7ff) - 1023;
+      if (x[0] == 0.0) e_n = 0;
+      sc_n = pow2i(-e_n);
+      elow_n = (int)(E + e_n);
+      sE_n = __shfl_up_sync(0xffffffffu, elow_n, 1);
+      asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a_er + (((p + 1) & (ST_NJ - 1)) * 32) * 4),
+                   "r"((unsigned)elow_n + (0x80000000u - 1023u)));
     }
-    strip_steps<K, HAS_V, false, CP, RS, ST_RB>(x, ma, nm1, yin, scn, bnd + ST_RB, take_bnd, write_out,
-                                                 xr + ST_RB * CP, yr + ST_RB * 32, outp + ST_RB);
+    strip_steps<K, HAS_V, false, CP, RS, false>(x, ma, nm1, yin, 0.0, scn, nb_addr, nb_stride, write_out,
+                                                xr + ST_RB * CP * 8, yr + (HAS_V ? ST_RB * 32 * 8 : 0),
+                                                outp + ST_RB * 8);
     ST_TICK(tk4);
     // ---- publish: at most two consumer batches complete per producer batch ----
     __syncwarp();
@@ -442,28 +523,26 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
       if (qd >= g.QT) qd = g.QT - 1;
       int q2slot = q1slot + 1;
       if (q2slot == NB) q2slot = 0;
-      mbar_arrive_if(&sb.full[q1slot], lane0 && qsent + 1 <= qd);
-      mbar_arrive_if(&sb.full[q2slot], lane0 && qsent + 2 <= qd);
+      mbar_arrive_if(a_full + q1slot * 8, lane0 && qsent + 1 <= qd);
+      mbar_arrive_if(a_full + q2slot * 8, lane0 && qsent + 2 <= qd);
       const int adv = qd - qsent;  // 0, 1 or 2
       if (adv > 0) {
         qsent = qd;
         q1slot += adv;
         if (q1slot >= NB) q1slot -= NB;
       }
-      st_shared_if(&rin_->taken, p + g.delta, lane0 && has_left);
-      st_shared_if(&rout_->written, p, write_out);
+      sts_s32_if(a_in_taken, p + g.delta, take_bnd);
+      sts_s32_if(a_out_written, p, write_out);
     }
     rows += ST_B;
     s0 += 2;
     if (s0 >= NB) {
       s0 = 0;
-      gen_need++;
+      gen_need += U;
     }
     ST_TICK(tk5);
-    ST_ACC(0, tk1, tk0);   // wait: ring slots free
-    ST_ACC(1, tk1b, tk1);  // wait: boundary in
-    ST_ACC(2, tk2, tk1b);  // wait: boundary out
-    ST_ACC(3, tk3, tk2);   // renormalise + batch set-up
+    ST_ACC(0, tk2, tk0);   // flow control
+    ST_ACC(3, tk3, tk2);   // batch set-up
     ST_ACC(4, tk4, tk3);   // the steps
     ST_ACC(5, tk5, tk4);   // publish
   }
@@ -485,8 +564,8 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
 
 // ---- consumer ----------------------------------------------------------------------------------------
 template <int K, int G, bool HAS_S, bool HAS_V, typename OutT>
-__device__ void strip_consumer(const StripParams &P, StripSub<K, G, HAS_V> &sb, const LogTabEntry *logtab,
-                               const StripGeom &g, int lane, const StripTable &tb) {
+__device__ void strip_consumer(const StripParams &P, StripSub<K, G, HAS_V> &sb, const double *logtab,
+                               const StripGeom &g, int lane, const StripTable &tb, const int ci, const int ncs) {
   using Cfg = StripCfg<K, G, HAS_V>;
   constexpr int CP = Cfg::CP, NB = Cfg::NB;
   const int M = P.M;
@@ -497,20 +576,34 @@ __device__ void strip_consumer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
   const bool first_strip = (g.rs == 0);
   const unsigned ld32 = (unsigned)P.ld;  // 8 rows x ld elements stay far below 2^32
 
-  for (;;) {
-    int q = 0;
-    if (lane == 0) q = atomicAdd(&sb.next_q, 1);
-    q = __shfl_sync(0xffffffffu, q, 0);
-    if (q >= g.QT) break;
+#ifdef STB_PROFILE_PRODUCER
+  long long cacc[4] = {0, 0, 0, 0};
+  long long ct_prev = clock64();
+#define ST_CTICK(slot)                  \
+  {                                     \
+    const long long ct_now = clock64(); \
+    cacc[slot] += ct_now - ct_prev;     \
+    ct_prev = ct_now;                   \
+  }
+#else
+#define ST_CTICK(slot)
+#endif
+  // The unit of work is 8 rows x 32 columns, dealt to the strip's consumers round-robin (unit u
+  // = q*U + kk goes to consumer u % ncs): no claim traffic at all, and the U column blocks of a
+  // row batch are worked on by U warps at once, so the batch's ring slot is free again after ONE
+  // block's latency -- a whole batch per warp held it ~K times longer and starved the producer of
+  // ring space.  Each finished unit counts the slot's release word up by one.
+  const int U = (cvalid + 31) >> 5;
+  int q = ci / U, kk = ci - q * U;
+  const int dq = ncs / U, dk = ncs - dq * U;
+  for (; q < g.QT;) {
     const int slot = q % NB;
+    ST_CTICK(0);
     if (!mbar_wait<ST_CONS_SLEEP>(&sb.full[slot], (unsigned)(q / NB) & 1u, P.abort_flag)) return;
+    ST_CTICK(1);  // wait for the rows
     const int r0 = q * ST_RB;
     const bool fast = (r0 >= cvalid - 1) && (r0 + ST_RB <= g.R);
-    // not unrolled: the body is ~250 instructions; K copies of it overflow the instruction cache
-    // and the misses stall every warp of the SM, the producers included
-#pragma unroll 1
-    for (int kk = 0; kk < K; kk++) {
-      if (32 * kk >= cvalid) break;
+    {
       const int col = lane + 32 * kk;
       const int pl = col / K;
       const int kq = col % K;
@@ -532,7 +625,7 @@ __device__ void strip_consumer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
           const unsigned Eb = sb.ering[((j0 + 1) & (ST_NJ - 1)) * 32 + pl];
           double v[ST_RB];
 #pragma unroll
-          for (int i = 0; i < ST_RB; i++) v[i] = log_scaled_i(xv[i], (i >= thr) ? Eb : Ea, logtab);
+          for (int i = 0; i < ST_RB; i++) v[i] = log_scaled_r<LOGTAB_REP8>(xv[i], (i >= thr) ? Eb : Ea, logtab);
           if (lane_ok) {
             OutT *pS = tabS + cell0;
 #pragma unroll
@@ -562,7 +655,7 @@ __device__ void strip_consumer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
           const size_t off = cell0 + (size_t)i * P.ld;
           if (HAS_S) {
             const int j = (toff + i) >> ST_SH;
-            const double v = log_scaled_i(xv, sb.ering[(j & (ST_NJ - 1)) * 32 + pl], logtab);
+            const double v = log_scaled_r<LOGTAB_REP8>(xv, sb.ering[(j & (ST_NJ - 1)) * 32 + pl], logtab);
             st_out(tabS + off, v);
             if (first_strip && col == 0) tb.s1[r] = v;
           }
@@ -575,8 +668,24 @@ __device__ void strip_consumer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
     }
     __syncwarp();
     asm volatile("" ::: "memory");
-    if (lane == 0) st_vol(&sb.empty_gen[slot], q / NB + 1);
+    if (lane == 0) atomicAdd(&sb.empty_gen[slot], 1);
+    ST_CTICK(2);  // the unit
+    q += dq;
+    kk += dk;
+    if (kk >= U) {
+      kk -= U;
+      q++;
+    }
+#ifdef STB_PROFILE_PRODUCER
+    cacc[3] += 1;
+#endif
   }
+#ifdef STB_PROFILE_PRODUCER
+  if (lane == 0 && P.dbg) {
+    long long *d = P.dbg + 1024 * 8 + ((size_t)blockIdx.x * ST_WARPS + (threadIdx.x >> 5)) * 4;
+    for (int i = 0; i < 4; i++) d[i] = cacc[i];
+  }
+#endif
 }
 
 // ---- loader / flusher: the CTA boundary through an L2-resident ring -----------------------------------
@@ -693,7 +802,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 1) fill_strip_kernel(const Stri
   const StripTable tb = P.tables[table];
   const bool cta_left = cta > 0, cta_right = strip0 + nloc < P.P;
 
-  for (int i = threadIdx.x; i < LOGTAB_N; i += blockDim.x) sm.logtab[i] = P.logtab[i];
+  for (int i = threadIdx.x; i < LOGTAB_N * LOGTAB_REP8; i += blockDim.x) sm.logtab[i] = P.logtab[i / LOGTAB_REP8];
   if (threadIdx.x < G) {
     auto &sb = sm.sub[threadIdx.x];
     for (int s = 0; s < Cfg::NB; s++) {
@@ -702,6 +811,8 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 1) fill_strip_kernel(const Stri
     }
     sb.next_q = 0;
   }
+  // boundary rings start as zeros: a strip without a left neighbour reads its (unused) ring
+  for (int i = threadIdx.x; i < (G + 1) * ST_NBR * ST_B; i += blockDim.x) sm.ring[i / (ST_NBR * ST_B)].x[i % (ST_NBR * ST_B)] = 0.0;
   if (threadIdx.x <= G) {
     // ring g feeds strip strip0+g, whose first batch reads batch delta: earlier batches count as taken
     const int rg = threadIdx.x, st = strip0 + rg;
@@ -737,19 +848,36 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 1) fill_strip_kernel(const Stri
     // the sub-partitions without a producer; a producer's own sub-partition takes only `spread`
     // of them, so that the recurrence keeps most of its issue slots and FP64 pipe.
     // consumer index c: warps on the free sub-partitions first, then rows 1..spread of the
-    // producers' sub-partitions (minus the two helper warps)
-    const int sp = warp & 3, row = warp >> 2;
-    int c;
-    if (sp >= G) {
-      c = row * (4 - G) + (sp - G);
-    } else {
-      if (G < 4 && row > P.spread) return;
-      c = 4 * (4 - G) + (row - 1) * G + sp - (warp > ST_LOADER) - (warp > ST_FLUSHER);
+    // producers' sub-partitions (the two helper warps excluded)
+    int c = -1, ntot = 0;
+    {
+      int nfree = 0, nshared = 0, mine = -1;
+      bool mine_free = false;
+      for (int w = G; w < ST_WARPS; w++) {
+        if (w == ST_LOADER || w == ST_FLUSHER) continue;
+        const bool fr = (w & 3) >= G;
+        if (!fr && G < 4 && (w >> 2) > P.spread) continue;
+        if (w == warp) {
+          mine = fr ? nfree : nshared;
+          mine_free = fr;
+        }
+        if (fr)
+          nfree++;
+        else
+          nshared++;
+      }
+      if (mine >= 0) c = mine_free ? mine : nfree + mine;
+      ntot = nfree + nshared;
     }
+    if (c < 0) return;
     const int gi = c % G, ci = c / G;
-    if (gi < nloc && ci < Cfg::NB - 1 && ci < P.ncons) {
+    // consumers serving strip gi: indices gi, gi+G, ... below ntot, at most NB-1 and P.ncons of them
+    int ncs = (ntot - gi + G - 1) / G;
+    if (ncs > Cfg::NB - 1) ncs = Cfg::NB - 1;
+    if (ncs > P.ncons) ncs = P.ncons;
+    if (gi < nloc && ci < ncs) {
       const StripGeom g = strip_geom(P, strip0 + gi);
-      strip_consumer<K, G, HAS_S, HAS_V, OutT>(P, sm.sub[gi], sm.logtab, g, lane, tb);
+      strip_consumer<K, G, HAS_S, HAS_V, OutT>(P, sm.sub[gi], sm.logtab + (lane & (LOGTAB_REP8 - 1)), g, lane, tb, ci, ncs);
     }
   }
 }
@@ -759,7 +887,7 @@ struct StripState {
   uint4 *gring;
   int *gctr;  // [cap] taken, then the abort flag at [cap]
   int cap;    // CTA boundaries the buffers can serve
-  LogTabEntry *logtab;
+  double *logtab;  // device, LOGTAB_N doubles
   StripTable *tables;  // device array
   int tables_cap;
   long long *dbg;  // STB_PROFILE_PRODUCER builds only
@@ -775,17 +903,16 @@ inline void strip_state_free(StripState *st) {
 }
 
 inline size_t strip_state_bytes(const StripState *st) {
-  return (size_t)st->cap * ST_NBG * ST_GE * sizeof(uint4) + (st->cap ? ((size_t)st->cap + 1) * sizeof(int) : 0) + (st->logtab ? LOGTAB_N * sizeof(LogTabEntry) : 0) +
+  return (size_t)st->cap * ST_NBG * ST_GE * sizeof(uint4) + (st->cap ? ((size_t)st->cap + 1) * sizeof(int) : 0) + (st->logtab ? LOGTAB_N * sizeof(double) : 0) +
          (size_t)st->tables_cap * sizeof(StripTable);
 }
 
 inline cudaError_t strip_state_prepare(StripState *st, int nbound, int ntables) {
   cudaError_t e;
   if (!st->logtab) {
-    LogTabEntry h[LOGTAB_N];
-    logtab_host(h);
-    if ((e = cudaMalloc(&st->logtab, sizeof h)) != cudaSuccess) return e;
-    if ((e = cudaMemcpy(st->logtab, h, sizeof h, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&st->logtab, LOGTAB_N * sizeof(double))) != cudaSuccess) return e;
+    logtab8_build_kernel<<<(LOGTAB_N + 127) / 128, 128>>>(st->logtab);
+    if ((e = cudaDeviceSynchronize()) != cudaSuccess) return e;
   }
   if (nbound > st->cap) {
     cudaFree(st->gring);
@@ -928,12 +1055,12 @@ inline int strip_fill(StripState *st, const StripFillArgs &A, cudaStream_t strea
   P.logtab = st->logtab;
   P.ncons = 64;
   if (const char *s = getenv("STB_STRIP_CONS")) P.ncons = atoi(s);
-  P.spread = 1;
+  P.spread = 1;  // consumer warps allowed on a producer's sub-partition (measured best: 1)
   if (const char *s = getenv("STB_STRIP_SPREAD")) P.spread = atoi(s);
   P.dbg = NULL;
 #ifdef STB_PROFILE_PRODUCER
-  if (!st->dbg) cudaMalloc(&st->dbg, 1024 * 8 * sizeof(long long));
-  cudaMemsetAsync(st->dbg, 0, 1024 * 8 * sizeof(long long), stream);
+  if (!st->dbg) cudaMalloc(&st->dbg, (1024 * 8 + 1024 * ST_WARPS * 4) * sizeof(long long));
+  cudaMemsetAsync(st->dbg, 0, (1024 * 8 + 1024 * ST_WARPS * 4) * sizeof(long long), stream);
   P.dbg = st->dbg;
 #endif
   for (int t0 = 0; t0 < A.ntables && e == cudaSuccess; t0 += per_launch) {
@@ -963,8 +1090,16 @@ inline int strip_fill(StripState *st, const StripFillArgs &A, cudaStream_t strea
       if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
 #ifdef STB_PROFILE_PRODUCER
       if (e == cudaSuccess && getenv("STB_PROFILE_PRINT")) {
-        static long long h[1024 * 8];
+        static long long h[1024 * 8 + 1024 * ST_WARPS * 4];
         cudaMemcpy(h, st->dbg, sizeof h, cudaMemcpyDeviceToHost);
+        for (int c : {0, nctas / 2}) {
+          for (int w = 0; w < ST_WARPS; w++) {
+            const long long *d = h + 1024 * 8 + ((size_t)c * ST_WARPS + w) * 4;
+            if (c < 1024 && d[3] > 0)
+              fprintf(stderr, "cta %3d consumer warp %2d units %6lld cycles/unit: claim %.0f wait %.0f work %.0f\n", c, w, d[3],
+                      (double)d[0] / d[3], (double)d[1] / d[3], (double)d[2] / d[3]);
+          }
+        }
         const int show[6] = {0, 1, 2, nctas / 2, nctas - 2, nctas - 1};
         for (int si = 0; si < 6; si++) {
           const int c = show[si];
@@ -974,7 +1109,7 @@ inline int strip_fill(StripState *st, const StripFillArgs &A, cudaStream_t strea
             const double nb = (double)d[6];
             if (nb <= 0 || (size_t)c * pl.G + gi >= 1024) continue;
             fprintf(stderr,
-                    "cta %3d producer %d batches %6.0f cycles/batch: slot-wait %.0f in-wait %.0f out-wait %.0f setup %.0f "
+                    "cta %3d producer %d batches %6.0f cycles/batch: flow-control %.0f - %.0f - %.0f setup %.0f "
                     "steps %.0f publish %.0f | busy %.1f us\n",
                     c, gi, nb, d[0] / nb, d[1] / nb, d[2] / nb, d[3] / nb, d[4] / nb, d[5] / nb, d[7] / 1e3);
           }
