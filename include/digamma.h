@@ -12,10 +12,15 @@ extern "C" {
 double digammaRN(double x);   /* Neal's series, the reference's default digamma (lib/digamma.c:31-48) */
 double MLdigamma(double x);   /* x > 0 */
 double MLtrigamma(double x);  /* x > 0 */
+double MLtetragamma(double x);  /* second derivative of psi, x > 0 */
+double MLpentagamma(double x);  /* third derivative of psi, x > 0 */
+double MLpsigamma(double x, double deriv); /* order round(deriv) in 0..3 (lib/polygamma.c:502-523); NaN beyond */
 double digammaInv(double x);  /* Minka start + 5 Newton steps (lib/digammainv.c:27-38) */
 
 #define digamma(x) MLdigamma(x)
 #define trigamma(x) MLtrigamma(x)
+#define tetragamma(x) MLtetragamma(x)
+#define pentagamma(x) MLpentagamma(x)
 
 #ifdef __cplusplus
 }

@@ -66,9 +66,21 @@ def lib() -> C.CDLL:
     L.samplea.restype = d
     L.samplea.argtypes = [d, C.c_int, ip, u32p, C.POINTER(u32p), C.POINTER(C.POINTER(C.c_uint16)), vp, dp, vp,
                           C.c_int, C.c_int]
-    for name in ("gsl_rng_gaussian_ziggurat", "gsl_rng_gamma", "digammaRN", "MLdigamma", "MLtrigamma", "digammaInv"):
+    for name in ("gsl_rng_gaussian_ziggurat", "gsl_rng_gamma", "digammaRN", "MLdigamma", "MLtrigamma", "digammaInv",
+                 "MLtetragamma", "MLpentagamma"):
         f = getattr(L, name)
         f.restype, f.argtypes = d, [d]
+    L.MLpsigamma.restype, L.MLpsigamma.argtypes = d, [d, d]
+    # closed forms beside the tables (include/sapprox.h, lgamma.h)
+    L.S_approx.restype, L.S_approx.argtypes = d, [C.c_int, C.c_int, C.c_float]
+    L.S_approx_da.restype, L.S_approx_da.argtypes = d, [C.c_int, C.c_int, C.c_float]
+    L.gammadiff.restype, L.gammadiff.argtypes = d, [C.c_int, d, d]
+    L.psidiff.restype, L.psidiff.argtypes = d, [C.c_int, d, d]
+    for kind in "gpq":
+        getattr(L, kind + "cache_init").restype = None
+        getattr(L, kind + "cache_init").argtypes = [vp, d]
+        getattr(L, kind + "cache_value").restype = d
+        getattr(L, kind + "cache_value").argtypes = [vp, C.c_int]
     L.gsl_rng_beta.restype, L.gsl_rng_beta.argtypes = d, [d, d]
     L.stb_rng48_state.restype, L.stb_rng48_state.argtypes = C.c_uint64, [C.c_long]
     L.stb_rng48_drand.restype, L.stb_rng48_drand.argtypes = d, [u64p]

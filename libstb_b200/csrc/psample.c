@@ -27,6 +27,19 @@
 double digammaRN(double x) { return stb_digammaRN(x); }
 double MLdigamma(double x) { return stb_digamma(x); }
 double MLtrigamma(double x) { return stb_trigamma(x); }
+double MLtetragamma(double x) { return stb_tetragamma(x); }
+double MLpentagamma(double x) { return stb_pentagamma(x); }
+double MLpsigamma(double x, double deriv) {
+  /* lib/polygamma.c:502-523 rounds the order to the nearest integer; orders 0..3 are what libstb uses */
+  if (isnan(x)) return x;
+  switch ((int)floor(deriv + 0.5)) {
+    case 0: return stb_digamma(x);
+    case 1: return stb_trigamma(x);
+    case 2: return stb_tetragamma(x);
+    case 3: return stb_pentagamma(x);
+    default: return NAN;
+  }
+}
 double digammaInv(double x) { return stb_digamma_inv(x); }
 
 /* ------------------------------------------------------------------------------------------ */
