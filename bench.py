@@ -66,13 +66,18 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
             return
         self.thread = threading.Thread(target=self._pump, daemon=True)
         self.thread.start()
-        time.sleep(0.3)  # let the first samples arrive before the timed region opens
+
+    def wait_first(self, timeout=8.0):
+        """block until nvidia-smi has delivered its first sample (its start-up can take seconds)"""
+        t_end = time.time() + timeout
+        while self.proc and not self.rows and time.time() < t_end:
+            time.sleep(0.02)
 
     def _pump(self):
         for line in self.proc.stdout:
@@ -83,7 +88,10 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.12)
         self.proc.terminate()
+        # samples inside the timed region; a region shorter than the sampling period takes the
+        # samples within 0.3 s of it (warm-up / extras run the same kernel at the same clocks)
         rows = [r for t, r in self.rows if t0 - 0.06 <= t <= t1 + 0.06 and len(r) >= 9] or \
+               [r for t, r in self.rows if t0 - 0.3 <= t <= t1 + 0.3 and len(r) >= 9] or \
                [r for _, r in self.rows if len(r) >= 9]
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
@@ -283,6 +291,21 @@ def run_extras():
         res["cpu_reference"] = {"samples_per_s": 6 / (time.perf_counter() - t0), "cores": 1, "chains": 3,
                                 "a_draws_match": bool(ok)}
     out["config4_samplers"] = res
+    # --- config 2 in the other storage modes (S-only, V-only, S+V, FP64 and S_FLOAT) ---
+    S, V, F = stb.S_STABLE, stb.S_UVTABLE, stb.S_FLOAT
+    cS, cV = cells_S(N_ROWS, M_COLS), M_COLS * (M_COLS - 1) // 2 + (N_ROWS - M_COLS) * (M_COLS - 1)
+    var = {}
+    for name, fl, ncell, bpc in (("S+V f64", S | V, cS + cV, 8), ("V f64", V, cV, 8), ("S f32", S | F, cS, 4),
+                                 ("S+V f32", S | V | F, cS + cV, 4)):
+        tv = stb.Table(N_ROWS, M_COLS, N_ROWS, M_COLS, DISCOUNT, fl | stb.S_NOMIRROR)
+        ms = []
+        for _ in range(3):
+            tv.remake(DISCOUNT)
+            ms.append(tv.last_fill_ms)
+        tv.free()
+        best = min(ms)
+        var[name] = {"kernel_ms": best, "cells_per_s": ncell / (best * 1e-3), "hbm_frac": ncell * bpc / (best * 1e-3) / 1e9 / 6544.7}
+    out["config2_variants"] = var
     return out
 
 
@@ -322,6 +345,9 @@ def run_own(args):
     u32p, dp = C.POINTER(C.c_uint32), C.POINTER(C.c_double)
     n_p, m_p, out_p = C.cast(n_h.data_ptr(), u32p), C.cast(m_h.data_ptr(), u32p), C.cast(out_h.data_ptr(), dp)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     t = stb.Table(N, M, N, M, a_rank, S_STABLE | S_NOMIRROR)  # first fill happens here (untimed)
 
     def step():
@@ -339,9 +365,9 @@ def run_own(args):
 
     for _ in range(max(args.warmup, 3) if not args.allow_short_warmup else args.warmup):
         step()
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.wait_first()
+        step()  # the GPU is busy while the sampler's period elapses
     barrier()
     t0 = time.time()
     w0 = time.perf_counter()
