@@ -1,9 +1,9 @@
-set -x
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest.log 2>&1; tail -3 gpurun_out/pytest.log
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
-python bench.py --steps 5 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; tail -c 600 gpurun_out/bench.err
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_launch.log 2>&1
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:fill_strip -s 4 -c 1 --csv --log-file gpurun_out/traffic.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_traffic.log 2>&1
-ncu --set full --import-source on --clock-control none -k regex:fill_strip -s 1 -c 1 -o gpurun_out/prof_r1c -f python tools/prof_fill.py 40000 20000 0.7 1 2 > gpurun_out/ncu_full.log 2>&1
-tail -2 gpurun_out/ncu_full.log
+tools/ubench_steps 2>&1 | head -16
+timeout 900 python -m pytest tests/test_table_gpu.py tests/test_sweep_gpu.py -m gpu -x -q 2>&1 | tail -3
+for k in 6 5; do
+echo "== K=$k"
+STB_STRIP_K=$k python tools/quick_time.py shape 200000 20000 0.7 1 2>&1 | tail -1
+STB_STRIP_K=$k python tools/quick_time.py shape 200000 20000 0.7 3 2>&1 | tail -1
+STB_STRIP_K=$k STB_STRIP_SPREAD=0 python tools/quick_time.py shape 200000 20000 0.7 1 2>&1 | tail -1
+done
+python tools/quick_sweep.py 2>&1 | tail -1

@@ -109,6 +109,7 @@ int main() {
   run<2, 0>(1, B); run<2, 0>(4, B);
   run<3, 0>(1, B); run<3, 0>(2, B); run<3, 0>(4, B);
   run<5, 0>(1, B); run<5, 0>(2, B); run<5, 0>(4, B);
+  run<6, 0>(1, B); run<6, 0>(2, B); run<4, 0>(1, B);
   run<7, 0>(1, B);
   printf("-- variants (K=5, 1 warp): 1 = no stores, 2 = no neighbour load, 4 = no coefficient adds\n");
   run<5, 1>(1, B); run<5, 2>(1, B); run<5, 3>(1, B); run<5, 4>(1, B); run<5, 5>(1, B); run<5, 6>(1, B); run<5, 7>(1, B);
