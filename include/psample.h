@@ -45,6 +45,18 @@ double sampleb(double b_in, int I, double shape, double scale, scnt_int *N, scnt
 #define SQUEEZEA 0.2
 
 /*
+ * Which sampler samplea / sampleb run.  The reference fixes this at compile time
+ * (lib/psample.h:37 PSAMPLE_ARS: ARS is its shipped default, the slice sampler the alternative);
+ * here it is a run-time switch, default STB_SAMPLER_SLICE.  With STB_SAMPLER_ARS the two behave
+ * like the reference's default build: arms_simple(3, ...) on [a-SQUEEZEA, a+SQUEEZEA] resp.
+ * [B_MIN, B_MAX], uniforms from rand() (lib/samplea.c:209-215, lib/sampleb.c:127-140).
+ * Returns the previous setting.  Process-wide, like the reference's generator state.
+ */
+#define STB_SAMPLER_SLICE 0
+#define STB_SAMPLER_ARS 1
+int stb_set_sampler(int which);
+
+/*
  * One MCMC update of the discount a (uniform prior on [A_MIN, A_MAX], moves squeezed to
  * +-SQUEEZEA).  n[i][k], t[i][k]: customers / tables of dish k in restaurant i (k < K[i]), or
  * the callback getval(&n,&t,i,k) when non-NULL; T[i] = sum_k t[i][k]; bpar[i]: concentration of

@@ -71,6 +71,12 @@ def lib() -> C.CDLL:
         f = getattr(L, name)
         f.restype, f.argtypes = d, [d]
     L.MLpsigamma.restype, L.MLpsigamma.argtypes = d, [d, d]
+    # adaptive rejection sampling (include/arms.h) and the sampler switch (include/psample.h)
+    L.arms_simple.restype = C.c_int
+    L.arms_simple.argtypes = [C.c_int, dp, dp, POST, vp, C.c_int, dp, dp]
+    L.arms.restype = C.c_int
+    L.arms.argtypes = [dp, C.c_int, dp, dp, POST, vp, dp, C.c_int, C.c_int, dp, dp, C.c_int, dp, dp, C.c_int, ip]
+    L.stb_set_sampler.restype, L.stb_set_sampler.argtypes = C.c_int, [C.c_int]
     # closed forms beside the tables (include/sapprox.h, lgamma.h)
     L.S_approx.restype, L.S_approx.argtypes = d, [C.c_int, C.c_int, C.c_float]
     L.S_approx_da.restype, L.S_approx_da.argtypes = d, [C.c_int, C.c_int, C.c_float]

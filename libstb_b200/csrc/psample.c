@@ -15,6 +15,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "arms.h"
 #include "digamma.h"
 #include "psample.h"
 #include "rng48.h"
@@ -169,6 +170,13 @@ static double bmax(double x, BLData *mp) { /* lib/sampleb.c:51-68: a few fixed-p
   return x_prime;
 }
 
+static int g_sampler = STB_SAMPLER_SLICE;
+int stb_set_sampler(int which) {
+  const int old = g_sampler;
+  g_sampler = which == STB_SAMPLER_ARS ? STB_SAMPLER_ARS : STB_SAMPLER_SLICE;
+  return old;
+}
+
 double sampleb(double b_in, int I, double shape, double scale, scnt_int *N, scnt_int *T, double apar, rngp_t rng,
                int loops, int verbose) {
   double Q, q, myb;
@@ -208,12 +216,23 @@ double sampleb(double b_in, int I, double shape, double scale, scnt_int *N, scnt
     bld.T = T;
     bld.apar = apar;
     bld.shape = shape;
-    myb = bmax(b_in, &bld);
-    if (verbose > 1) fprintf(stderr, "Max b (%lg,%lg) -> %lg\n", b_in, Q, myb);
-    initb[1] = B_MAX;
-    if (SliceSimple(&myb, bterms, initb, rng, loops, &bld)) {
-      fprintf(stderr, "SliceSimple error\n");
-      exit(1);
+    if (g_sampler == STB_SAMPLER_ARS) { /* lib/sampleb.c:127-140 */
+      initb[1] = b_in;
+      if (fabs(initb[1] - B_MAX) / B_MAX < 0.00001) initb[1] = B_MAX * 0.999 + B_MIN * 0.001;
+      if (fabs(initb[1] - B_MIN) / B_MIN < 0.00001) initb[1] = B_MIN * 0.999 + B_MAX * 0.001;
+      arms_simple(3, initb, initb + 2, bterms, &bld, 0, initb + 1, &myb);
+      if (myb < B_MIN || myb > B_MAX) {
+        fprintf(stderr, "Arms_simple(bpar) returned value out of bounds\n");
+        exit(1);
+      }
+    } else {
+      myb = bmax(b_in, &bld);
+      if (verbose > 1) fprintf(stderr, "Max b (%lg,%lg) -> %lg\n", b_in, Q, myb);
+      initb[1] = B_MAX;
+      if (SliceSimple(&myb, bterms, initb, rng, loops, &bld)) {
+        fprintf(stderr, "SliceSimple error\n");
+        exit(1);
+      }
     }
     if (verbose > 1) fprintf(stderr, "Sample b ~ G(%lg) = %lf\n", Q, myb);
   }
@@ -319,11 +338,19 @@ double samplea(double mya, int I, int *K, scnt_int *T, scnt_int **n, stcnt_int *
   }
   ald.first[I] = j;
   ald.cnt = j;
-  /* the slice sampler may move anywhere in [inita[0], A_MAX] (lib/samplea.c:217-218) */
-  inita[1] = A_MAX;
-  if (SliceSimple(&mya, aterms, inita, rng, loops, &ald)) {
-    fprintf(stderr, "SliceSimple error\n");
-    exit(1);
+  if (g_sampler == STB_SAMPLER_ARS) { /* lib/samplea.c:209-215 */
+    arms_simple(3, inita, inita + 2, aterms, &ald, 0, inita + 1, &mya);
+    if (mya < inita[0] || mya > inita[2]) {
+      fprintf(stderr, "Arms_simple(apar) returned value out of bounds\n");
+      exit(1);
+    }
+  } else {
+    /* the slice sampler may move anywhere in [inita[0], A_MAX] (lib/samplea.c:217-218) */
+    inita[1] = A_MAX;
+    if (SliceSimple(&mya, aterms, inita, rng, loops, &ald)) {
+      fprintf(stderr, "SliceSimple error\n");
+      exit(1);
+    }
   }
   if (ald.S) S_free(ald.S);
   free(ald.first);

@@ -181,3 +181,36 @@ def test_config4_recipe_small_slice():
     libc.srand48(12345)
     a_ref = R.samplea(float(a0[0]), *cts.args(), None, bpar.ctypes.data_as(dp), None, 1, 0)
     assert a1[0] == pytest.approx(a_ref, rel=1e-9)
+
+
+@pytest.mark.skipif(not os.path.exists(harness.REF_SO), reason="reference build not present")
+def test_scalar_samplea_ars_mode_matches_reference_default_build():
+    """STB_SAMPLER_ARS: samplea runs arms_simple over the GPU table density, like the reference's
+    default (ARS) build (lib/samplea.c:209-215).  Same srand() seed: same number of uniforms
+    consumed and draws within 1e-9 (the density's last bits differ: device table vs libm)."""
+    L = stb.lib()
+    R = C.CDLL(harness.REF_SO)  # default build = ARS configuration
+    d, u32p = C.c_double, C.POINTER(C.c_uint32)
+    R.samplea.restype = d
+    R.samplea.argtypes = [d, C.c_int, C.POINTER(C.c_int), u32p, C.POINTER(u32p), C.POINTER(C.POINTER(C.c_uint16)),
+                          C.c_void_p, C.POINTER(d), C.c_void_p, C.c_int, C.c_int]
+    libc.srand.argtypes = [C.c_uint]
+    libc.rand.restype = C.c_int
+    cts = _counts(43, I=12, K=10, nmax=400)
+    bpar = np.full(cts.I, 10.0)
+    dp = C.POINTER(C.c_double)
+    old = L.stb_set_sampler(1)
+    try:
+        a_ref = a_our = 0.5
+        for step in range(6):
+            libc.srand(900 + step)
+            a_ref = R.samplea(a_ref, *cts.args(), None, bpar.ctypes.data_as(dp), None, 1, 0)
+            r_ref = libc.rand()
+            libc.srand(900 + step)
+            a_our = L.samplea(a_our, *cts.args(), None, bpar.ctypes.data_as(dp), None, 1, 0)
+            assert libc.rand() == r_ref, "different numbers of uniforms consumed"
+            assert a_our == pytest.approx(a_ref, rel=1e-9)
+            assert 0.01 <= a_our <= 0.98
+            a_our = a_ref
+    finally:
+        L.stb_set_sampler(old)
