@@ -43,3 +43,18 @@ files=""
 for s in $SRC polygamma; do files="$files $TMP/$s.c"; done
 $CC $CFLAGS -shared -o "$OUT/libstb_ref_slice.so" $files -lm -lpthread
 echo "built $OUT/libstb_ref.so $OUT/libstb_ref_slice.so"
+
+# --- the reference's own test programs (test/list.c, test/demo.c, test/check.c), UNMODIFIED ---
+#   oracle/_ref/ref_list      list.c linked with the reference library: generates tests/golden/list_*.txt
+#   oracle/_ref/dropin_{list,demo,check}
+#                             the same sources compiled against THIS repo's include/ and linked with
+#                             libstb_b200.so: the drop-in proof (they need a GPU to run)
+$CC -O2 -w -I"$REF/lib" "$REF/test/list.c" -o "$OUT/ref_list" "$OUT/libstb_ref.so" -Wl,-rpath,'$ORIGIN' -lm
+LIBDIR="$HERE/../libstb_b200/lib"
+if [ -f "$LIBDIR/libstb_b200.so" ]; then
+  for p in list demo check; do
+    $CC -O2 -w -I"$HERE/../include" "$REF/test/$p.c" -o "$OUT/dropin_$p" -L"$LIBDIR" -lstb_b200 \
+        -Wl,-rpath,'$ORIGIN/../../libstb_b200/lib' -lm
+  done
+  echo "built $OUT/ref_list and $OUT/dropin_{list,demo,check}"
+fi
