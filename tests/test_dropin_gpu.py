@@ -68,3 +68,29 @@ def test_list_program_output_matches_reference(case):
         if len(nw) != len(ng) or not all(_numbers_match(a, b) for a, b in zip(nw, ng)):
             bad.append((lw, lg))
     assert not bad, bad[:5]
+
+
+@pytest.mark.gpu
+def test_demo_and_check_programs_run_end_to_end():
+    """test/demo.c (simulated PYP hierarchy: Gibbs on table counts with S_V / S_U, samplea and
+    sampleb every few cycles) and test/check.c (table-indicator sampler, a/b sampling) run to
+    completion on the GPU engine and report estimates inside the samplers' bounds.  Their random
+    decisions depend on the last bits of the table values, so only the summaries are checked."""
+    if not (os.path.exists(DROPIN["demo"]) and os.path.exists(DROPIN["check"])):
+        pytest.skip("oracle/_ref/dropin_* not built")
+    demo = subprocess.run([DROPIN["demo"], "-a", "0.3", "-b", "5", "-N", "200", "-C", "50", "-I", "10", "-H", "10",
+                           "-s", "7"], capture_output=True, text=True, timeout=300)
+    assert demo.returncode == 0, demo.stderr[-2000:]
+    out = demo.stdout + demo.stderr
+    a = float(re.search(r"^a=([0-9.]+)", out, re.M).group(1))
+    b = float(re.search(r"^b=([0-9.]+)", out, re.M).group(1))
+    assert 0.01 <= a <= 0.98 and 0.01 <= b <= 2000
+    assert len(re.findall(r"^T\[\d\]=", out, re.M)) == 3
+    chk = subprocess.run([DROPIN["check"], "-a", "0.3", "-b", "5", "-N", "200", "-C", "20", "-I", "5", "-H", "5",
+                          "-s", "7", "-STI"], capture_output=True, text=True, timeout=300)
+    assert chk.returncode == 0, chk.stderr[-2000:]
+    out = chk.stdout + chk.stderr
+    a = float(re.search(r"Run ave a: = ([0-9.]+)", out).group(1))
+    b = float(re.search(r"Run ave b: = ([0-9.]+)", out).group(1))
+    T = float(re.search(r"Run ave T: = ([0-9.]+)", out).group(1))
+    assert 0.01 <= a <= 0.98 and 0.01 <= b <= 2000 and 5 <= T <= 200
