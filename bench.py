@@ -329,6 +329,7 @@ def run_own(args):
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = stb.lib()
     N, M = args.rows, args.cols
