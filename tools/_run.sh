@@ -1,3 +1,8 @@
-(time timeout 120 oracle/_ref/dropin_demo -a 0.3 -b 5 -N 200 -C 50 -I 10 -H 10 -s 7) 2>&1 | tail -25
-echo ======
-(time timeout 120 oracle/_ref/dropin_check -a 0.3 -b 5 -N 200 -C 20 -I 5 -H 5 -s 7 -STI) 2>&1 | tail -25
+timeout 900 python -m pytest tests/test_table_gpu.py tests/test_sweep_gpu.py tests/test_table_large_gpu.py -m gpu -x -q 2>&1 | tail -3
+for v in 64 20 200; do
+echo "== helper sleep $v"
+[ $v != 64 ] && export STB_B200_LIB=$PWD/libstb_b200/lib/hs$v/libstb_b200.so
+python tools/quick_time.py shape 200000 20000 0.7 1 2>&1 | tail -1
+python tools/quick_time.py shape 200000 20000 0.7 3 2>&1 | tail -1
+python tools/quick_sweep.py 2>&1 | tail -1
+done
