@@ -972,12 +972,13 @@ struct StripPlan {
 
 /*
  * Geometry for tables of M columns when `slots` CTAs are available per table.  The compiled
- * shapes are (K columns per lane, G strips per CTA) = (1,4), (5,1), (3,2), (7,1): up to 128, 160,
- * 192 and 224 columns per CTA, tried in that order (measured best first); the lane count is then trimmed so that the columns are
- * spread evenly and strip edges fall on 32-byte sectors of the table.
+ * shapes are (K columns per lane, G strips per CTA) = (5,1), (7,1), (1,4), (3,2): up to 160, 224,
+ * 128 and 192 columns per CTA, tried in that order (measured best first).
  */
 inline bool strip_plan(unsigned M, int slots, size_t elem_size, StripPlan *pl) {
-  static const int shapes[4][2] = {{1, 4}, {5, 1}, {3, 2}, {7, 1}};
+  // measured best first: ONE strip per CTA with 5 (up to 160 columns) or 7 (up to 224) columns per
+  // lane; the multi-strip shapes are kept for STB_STRIP_K experiments and the geometry-independence test
+  static const int shapes[4][2] = {{5, 1}, {7, 1}, {1, 4}, {3, 2}};
   int force_k = 0, force_l = 0;
   if (const char *s = getenv("STB_STRIP_K")) force_k = atoi(s);
   if (const char *s = getenv("STB_STRIP_L")) force_l = atoi(s);
@@ -986,12 +987,21 @@ inline bool strip_plan(unsigned M, int slots, size_t elem_size, StripPlan *pl) {
   for (int i = 0; i < 4; i++) {
     const int k = shapes[i][0], gg = shapes[i][1];
     if (force_k ? k != force_k : (unsigned)(32 * k * gg) < per_cta) continue;
-    unsigned want = (per_cta + (unsigned)gg - 1) / (unsigned)gg;  // columns per strip
-    if (want < 32u) want = M < 32u ? M : 32u;  // never narrower than a warp unless the table is
-    int L = (int)((want + (unsigned)k - 1) / (unsigned)k);
+    int L;
+    if (gg == 1) {
+      // Full warps and as FEW CTAs as the table needs beat an even spread over all SMs: the row rate
+      // is the producer's whatever the lane count, the consumers' 32-column units come out full,
+      // and every CTA boundary less is one hop less of pipeline lag (config 2: 143 x 140 columns
+      // 9.45 ms, 125 x 160 columns 9.16 ms; config 1: 8 CTAs of 4 x 32 columns 1.29 ms, 7 x 160 0.63 ms).
+      L = (int)((M + (unsigned)k - 1) / (unsigned)k);
+    } else {
+      unsigned want = (per_cta + (unsigned)gg - 1) / (unsigned)gg;  // columns per strip
+      if (want < 32u) want = M < 32u ? M : 32u;  // never narrower than a warp unless the table is
+      L = (int)((want + (unsigned)k - 1) / (unsigned)k);
+    }
     if (L > 32) L = 32;
     if (L < 1) L = 1;
-    while (L < 32 && ((size_t)L * k * elem_size) % 32 != 0) L++;
+    while (L < 32 && ((size_t)L * k * elem_size) % 32 != 0) L++;  // strip edges on 32-byte sectors
     if (force_l) L = force_l;
     pl->K = k;
     pl->G = gg;

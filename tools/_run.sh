@@ -1,8 +1,11 @@
-timeout 900 python -m pytest tests/test_table_gpu.py tests/test_sweep_gpu.py tests/test_table_large_gpu.py -m gpu -x -q 2>&1 | tail -3
-for v in 64 20 200; do
-echo "== helper sleep $v"
-[ $v != 64 ] && export STB_B200_LIB=$PWD/libstb_b200/lib/hs$v/libstb_b200.so
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 python tools/quick_time.py shape 200000 20000 0.7 1 2>&1 | tail -1
 python tools/quick_time.py shape 200000 20000 0.7 3 2>&1 | tail -1
+python tools/quick_time.py shape 200000 25000 0.7 1 2>&1 | tail -1
+python tools/quick_time.py shape 50000 5000 0.7 1 2>&1 | tail -1
+python tools/quick_time.py shape 10000 1000 0.5 3 2>&1 | tail -1
+python tools/quick_time.py shape 2000 300 0.5 3 2>&1 | tail -1
+python tools/quick_time.py shape 500 20 0.5 3 2>&1 | tail -1
 python tools/quick_sweep.py 2>&1 | tail -1
-done
+python tools/quick_sweep.py 5001 167 1036 2>&1 | tail -1
+python tools/_t.py 2>&1 | tail -2
