@@ -66,6 +66,10 @@ double stb_sweep_last_fill_ms(const stb_sweep_t *w);
 int stb_sweep_tables_in_flight(const stb_sweep_t *w);
 void stb_sweep_free(stb_sweep_t *w);
 
+/* frees device memory the batched samplers keep between calls (the sweep handle of the last
+ * stb_samplea_batch: one launch's worth of table slabs) */
+void stb_release_caches(void);
+
 /* device milliseconds of the most recent fill (CUDA events around the kernel) */
 double stb_last_fill_ms(const stable_t *sp);
 /* device address and row pitch (elements) of the S (which_V==0) or V slab; cell (n,m) at [(n-1)*ld+m-1] */

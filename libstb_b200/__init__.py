@@ -58,6 +58,7 @@ def lib() -> C.CDLL:
     L.stb_sweep_last_fill_ms.restype, L.stb_sweep_last_fill_ms.argtypes = d, [vp]
     L.stb_sweep_tables_in_flight.restype, L.stb_sweep_tables_in_flight.argtypes = C.c_int, [vp]
     L.stb_sweep_free.restype, L.stb_sweep_free.argtypes = None, [vp]
+    L.stb_release_caches.restype, L.stb_release_caches.argtypes = None, []
     # samplers (include/psample.h, srng.h, digamma.h)
     u64p, ip = C.POINTER(C.c_uint64), C.POINTER(C.c_int)
     POST = C.CFUNCTYPE(d, d, vp)

@@ -206,12 +206,46 @@ static int aterms_batch(void *ctx, const double *x, const int *chain, size_t cnt
   return 0;
 }
 
+/*
+ * The sweep handle (resident slabs for one launch's worth of tables: ~1 GB for the config-4 shape)
+ * is kept between calls -- an MCMC run calls samplea once per sweep with the same table extent,
+ * and allocating / freeing a gigabyte of device memory per call costs more than the evaluations.
+ * stb_release_caches() frees it.  (The samplers are not thread-safe in the reference either.)
+ */
+static struct {
+  stb_sweep_t *w;
+  unsigned N, M;
+} g_sweep_cache;
+
+void stb_release_caches(void) {
+  if (g_sweep_cache.w) stb_sweep_free(g_sweep_cache.w);
+  g_sweep_cache.w = NULL;
+}
+
+static stb_sweep_t *sweep_acquire(unsigned N, unsigned M) {
+  stb_sweep_t *w = g_sweep_cache.w;
+  if (w && g_sweep_cache.N == N && g_sweep_cache.M == M) {
+    g_sweep_cache.w = NULL;
+    return w;
+  }
+  stb_release_caches();
+  return stb_sweep_create(N, M, 0);
+}
+
+static void sweep_release(stb_sweep_t *w, unsigned N, unsigned M) {
+  stb_release_caches();
+  g_sweep_cache.w = w;
+  g_sweep_cache.N = N;
+  g_sweep_cache.M = M;
+}
+
 int stb_samplea_batch(double *a, size_t C, int I, const int *K, const scnt_int *T, scnt_int **n, stcnt_int **t,
                       const double *bpar, int bpar_per_chain, uint64_t *rng, int loops, stb_sample_stats *st) {
   double *lo = NULL, *hi = NULL;
   uint32_t *nn = NULL, *tt = NULL;
   size_t total = 0, cnt = 0, c;
   int i, k, maxn = 1, maxt = 1, rc = -1;
+  unsigned Mx = 0, Nx = 0;
   ABatch ab;
   memset(&ab, 0, sizeof ab);
   if (!C) return 0;
@@ -244,8 +278,9 @@ int stb_samplea_batch(double *a, size_t C, int I, const int *K, const scnt_int *
     }
   {
     /* the same clamps S_make applies (lib/stable.c:118-129) */
-    unsigned Mx = maxt < 10 ? 10u : (unsigned)maxt, Nx = (unsigned)maxn < Mx ? Mx : (unsigned)maxn;
-    ab.sweep = stb_sweep_create(Nx, Mx, 0);
+    Mx = maxt < 10 ? 10u : (unsigned)maxt;
+    Nx = (unsigned)maxn < Mx ? Mx : (unsigned)maxn;
+    ab.sweep = sweep_acquire(Nx, Mx);
   }
   if (!ab.sweep || stb_sweep_set_pairs(ab.sweep, nn, tt, cnt)) goto done;
   ab.ps = stb_cuda_pstat_create(I, T, NULL, bpar, bpar_per_chain ? C * (size_t)I : (size_t)I, C);
@@ -254,7 +289,7 @@ int stb_samplea_batch(double *a, size_t C, int I, const int *K, const scnt_int *
   ab.st = st;
   rc = slice_lockstep(a, C, lo, hi, rng, loops, aterms_batch, &ab, st);
 done:
-  if (ab.sweep) stb_sweep_free(ab.sweep);
+  if (ab.sweep) sweep_release(ab.sweep, Nx, Mx);
   if (ab.ps) stb_cuda_pstat_destroy(ab.ps);
   free(lo);
   free(hi);

@@ -339,8 +339,8 @@ struct stb_sweep_dev {
   double *s1;          // [T][N]
   stb::StripState strip;
   uint32_t *d_n, *d_m;
-  size_t npairs;
-  double *d_gather;    // [T][npairs]
+  size_t npairs, pairs_cap, gather_cap;
+  double *d_gather;    // [T][npairs], allocated when a gather is first asked for
   double *d_partial;   // [T][nblk]
   double *d_sum;       // [T]
   double *h_stage;     // pinned staging for sums
@@ -452,19 +452,21 @@ extern "C" int stb_cuda_sweep_tables_in_flight(const stb_sweep_dev_t *w) { retur
 
 extern "C" int stb_cuda_sweep_set_pairs(stb_sweep_dev_t *w, const uint32_t *n, const uint32_t *m, size_t npairs) {
   CK(cudaSetDevice(w->device));
-  cudaFree(w->d_n);
-  cudaFree(w->d_m);
-  cudaFree(w->d_gather);
-  cudaFree(w->d_partial);
-  w->d_n = w->d_m = NULL;
-  w->d_gather = w->d_partial = NULL;
   w->npairs = npairs;
   if (!npairs) return 0;
-  const size_t nblk = (npairs + 255) / 256;
-  CK(cudaMalloc(&w->d_n, npairs * sizeof(uint32_t)));
-  CK(cudaMalloc(&w->d_m, npairs * sizeof(uint32_t)));
-  CK(cudaMalloc(&w->d_gather, (size_t)w->T * npairs * sizeof(double)));
-  CK(cudaMalloc(&w->d_partial, (size_t)w->T * nblk * sizeof(double)));
+  if (npairs > w->pairs_cap) {  // buffers are kept across calls (a cached handle sees many pair sets)
+    cudaFree(w->d_n);
+    cudaFree(w->d_m);
+    cudaFree(w->d_partial);
+    w->d_n = w->d_m = NULL;
+    w->d_partial = NULL;
+    w->pairs_cap = 0;
+    const size_t nblk = (npairs + 255) / 256;
+    CK(cudaMalloc(&w->d_n, npairs * sizeof(uint32_t)));
+    CK(cudaMalloc(&w->d_m, npairs * sizeof(uint32_t)));
+    CK(cudaMalloc(&w->d_partial, (size_t)w->T * nblk * sizeof(double)));
+    w->pairs_cap = npairs;
+  }
   CK(cudaMemcpyAsync(w->d_n, n, npairs * sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
   CK(cudaMemcpyAsync(w->d_m, m, npairs * sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
   CK(cudaStreamSynchronize(w->stream));
@@ -481,6 +483,13 @@ extern "C" int stb_cuda_sweep_run(stb_sweep_dev_t *w, const double *a, size_t na
   if ((gather_out || sum_out) && !w->npairs) {
     snprintf(g_err, sizeof g_err, "stb_cuda_sweep_run: no look-up pairs set");
     return -1;
+  }
+  if (gather_out && w->npairs > w->gather_cap) {
+    cudaFree(w->d_gather);
+    w->d_gather = NULL;
+    w->gather_cap = 0;
+    CK(cudaMalloc(&w->d_gather, (size_t)w->T * w->npairs * sizeof(double)));
+    w->gather_cap = w->npairs;
   }
   std::vector<stb::StripTable> tabs((size_t)w->T);
   for (size_t j0 = 0; j0 < na; j0 += (size_t)w->T) {
