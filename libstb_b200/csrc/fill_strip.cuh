@@ -22,7 +22,8 @@
  *     address arithmetic; the G producers of a CTA sit on different SM sub-partitions.
  *   - Consumer warps claim 8-row batches (atomic counter per strip), take log / divide and write
  *     each row segment to HBM exactly once with coalesced 256-byte stores.  Producer -> consumer
- *     is one mbarrier per batch slot; consumer -> producer a generation word per slot.
+ *     is one progress word (the last batch whose steps are all in the ring); consumer -> producer
+ *     a count of finished units per ring slot.
  *   - The strip's last column goes to the next strip in batches of 16 rows with ONE exponent per
  *     batch: strips start their batch counters with a phase shift chosen so that the sender's
  *     and the receiver's batches line up, which makes the receiver's scale factor a per-batch
@@ -135,7 +136,8 @@ struct alignas(16) StripSub {  // per strip
   double yring[HAS_V ? (Cfg::RS + ST_RB) * 32 : 2];
   unsigned ering[ST_NJ * 32];  // E + 0x80000000 - 1023 (mod 2^32) per (producer batch, lane): log_scaled_i
   int pad0[2];
-  unsigned long long full[Cfg::NB];
+  int progress;  // last producer batch whose sixteen steps are all in the ring (-1: none yet)
+  int padp[3];
   int empty_gen[Cfg::NB];  // units (8 rows x 32 columns) of slot s finished so far: U per tenant batch
   int next_q;
   int pad[3];
@@ -148,49 +150,8 @@ struct StripSmem {
   BRing ring[G + 1];  // ring g feeds strip g; ring 0 is filled by the loader, ring G drained by the flusher
 };
 
-// ---- mbarrier ------------------------------------------------------------------------------------
+// ---- waits ---------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_test_wait(unsigned long long *bar, unsigned parity) {
-  unsigned ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-
-/*
- * Warp-collective blocking wait; false when the fill was aborted (watchdog / another role).
- * Polls with the non-blocking test_wait: the blocking try_wait parks the warp in hardware and was
- * measured to wake late (the hand-off then costs microseconds, not cycles).  SLEEP (ns) between
- * polls keeps waiting consumer warps from eating the issue slots of working ones.
- */
-template <int SLEEP>
-__device__ __forceinline__ bool mbar_wait(unsigned long long *bar, unsigned parity, int *abort_flag) {
-  if (mbar_test_wait(bar, parity)) return true;
-  const long long t0 = clock64();
-  unsigned spins = 0;
-  for (;;) {
-    if (SLEEP) __nanosleep(SLEEP);
-    if (mbar_test_wait(bar, parity)) return true;
-    if ((++spins & 1023u) == 0) {
-      const int bad = ld_vol(abort_flag) || (clock64() - t0 > FILL_WATCHDOG);
-      if (__any_sync(0xffffffffu, bad)) {
-        if ((threadIdx.x & 31) == 0) atomicExch(abort_flag, 1);
-        return false;
-      }
-    }
-  }
-}
 
 /*
  * Warp-collective wait until *ctr >= need (shared-memory or global counter).  Shared-memory
@@ -255,13 +216,6 @@ __device__ __forceinline__ StripGeom strip_geom(const StripParams &P, int strip)
   return g;
 }
 
-/* consumer batches that are complete once producer batch p is: q <= this (may be -1) */
-__device__ __forceinline__ int strip_qdone(int p, int phi, int L) {
-  // after batch p every lane has made rows 0 .. rows-1, rows = ST_B*(p+1) - phi - (L-1)
-  const int rows = ST_B * p + ST_B - phi - (L - 1);
-  return rows >= 0 ? rows / ST_RB - 1 : -1;
-}
-
 // ---- producer ----------------------------------------------------------------------------------------
 /*
  * Shared-memory accesses of the recurrence by 32-bit shared address with immediate offsets
@@ -302,15 +256,6 @@ __device__ __forceinline__ void sts_s32_if(unsigned a, int v, bool pred) {
       "r"(v), "r"((unsigned)pred)
       : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_if(unsigned bar, bool pred) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.u32 p, %1, 0;\n\t"
-      "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(bar),
-      "r"((unsigned)pred)
-      : "memory");
-}
-
 /*
  * Eight recurrence steps.  x[k]: the lane's K columns; the coefficient of column m_k in row n is
  * (n-1) - m_k a, formed per step from nm1 = n-1 and ma[k] = m_k a exactly like that (one rounding,
@@ -426,7 +371,7 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
   const unsigned a_yr = smem_u32(&sb.yring[HAS_V ? lane : 0]);
   const unsigned a_er = smem_u32(&sb.ering[lane]);
   const unsigned a_gen = smem_u32(&sb.empty_gen[0]);
-  const unsigned a_full = smem_u32(&sb.full[0]);
+  const unsigned a_prog = smem_u32(&sb.progress);
   const unsigned a_in_x = smem_u32(&rin->x[0]), a_in_e = smem_u32(&rin->e[0]);
   const unsigned a_in_written = smem_u32(&rin->written), a_in_taken = smem_u32(&rin->taken);
   const unsigned a_out_x = smem_u32(&rout->x[0]), a_out_e = smem_u32(&rout->e[0]);
@@ -443,13 +388,10 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
   double sc_n = 1.0;
   asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a_er), "r"(0x80000000u - 1023u));
 
-  int qsent = -1;                     // consumer batches released so far
-  int rows = ST_B - g.phi - (L - 1);  // rows 0..rows-1 are complete after the current batch
   int cvalid_p = P.M - g.rs;
   if (cvalid_p > P.C) cvalid_p = P.C;
   const int U = (cvalid_p + 31) >> 5;  // units per consumer batch (see strip_consumer)
   int s0 = 0, gen_need = 0;           // consumer slot pair of the batch, finished units it must show
-  int q1slot = 0;                     // slot of consumer batch qsent+1
   int c_in = -1, c_out = has_right ? lds_s32(a_out_taken) : 0;
 #ifdef STB_PROFILE_PRODUCER
   long long dbgacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -522,26 +464,13 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
                                                 xr + ST_RB * CP * 8, yr + (HAS_V ? ST_RB * 32 * 8 : 0),
                                                 outp + ST_RB * 8);
     ST_TICK(tk4);
-    // ---- publish: at most two consumer batches complete per producer batch ----
+    // ---- publish: ONE word says how far the ring is filled; consumers, flusher and loader work
+    // out from it what they may touch ----
     __syncwarp();
     asm volatile("" ::: "memory");
-    {
-      int qd = rows >= 0 ? (rows >> 3) - 1 : -1;
-      if (qd >= g.QT) qd = g.QT - 1;
-      int q2slot = q1slot + 1;
-      if (q2slot == NB) q2slot = 0;
-      mbar_arrive_if(a_full + q1slot * 8, lane0 && qsent + 1 <= qd);
-      mbar_arrive_if(a_full + q2slot * 8, lane0 && qsent + 2 <= qd);
-      const int adv = qd - qsent;  // 0, 1 or 2
-      if (adv > 0) {
-        qsent = qd;
-        q1slot += adv;
-        if (q1slot >= NB) q1slot -= NB;
-      }
-      sts_s32_if(a_in_taken, p + g.delta, take_bnd);
-      sts_s32_if(a_out_written, p, write_out);
-    }
-    rows += ST_B;
+    sts_s32_if(a_prog, p, lane0);
+    sts_s32_if(a_in_taken, p + g.delta, take_bnd);
+    sts_s32_if(a_out_written, p, write_out);
     s0 += 2;
     if (s0 >= NB) {
       s0 = 0;
@@ -564,9 +493,6 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
     d[5] = dbgacc[5];
   }
 #endif
-  // a partial last row batch never sees its eighth row: release it now that every row exists
-  if (lane0)
-    for (int q = qsent + 1; q < g.QT; q++) mbar_arrive(&sb.full[q % NB]);
 }
 
 // ---- consumer ----------------------------------------------------------------------------------------
@@ -603,10 +529,16 @@ __device__ void strip_consumer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
   const int U = (cvalid + 31) >> 5;
   int q = ci / U, kk = ci - q * U;
   const int dq = ncs / U, dk = ncs - dq * U;
+  int prog = -1;  // the producer's progress as last seen
   for (; q < g.QT;) {
     const int slot = q % NB;
     ST_CTICK(0);
-    if (!mbar_wait<ST_CONS_SLEEP>(&sb.full[slot], (unsigned)(q / NB) & 1u, P.abort_flag)) return;
+    // rows 8q .. 8q+7 of every lane are in the ring once the producer has finished the batch that
+    // holds step 8q+7 + (L-1) + phi (the last lane runs L-1 rows behind the first); a partial last
+    // row batch is complete with the last producer batch
+    int p_need = ((q * ST_RB + ST_RB - 1 + P.L - 1 + g.phi) >> ST_SH);
+    if (p_need > g.nbatch - 1) p_need = g.nbatch - 1;
+    if (!ctr_wait<false, ST_CONS_SLEEP>(&sb.progress, p_need, P.abort_flag, prog)) return;
     ST_CTICK(1);  // wait for the rows
     const int r0 = q * ST_RB;
     const bool fast = (r0 >= cvalid - 1) && (r0 + ST_RB <= g.R);
@@ -814,10 +746,8 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 1) fill_strip_kernel(const Stri
   for (int i = threadIdx.x; i < LOGTAB_N * LOGTAB_REP8; i += blockDim.x) sm.logtab[i] = P.logtab[i / LOGTAB_REP8];
   if (threadIdx.x < G) {
     auto &sb = sm.sub[threadIdx.x];
-    for (int s = 0; s < Cfg::NB; s++) {
-      mbar_init(&sb.full[s], 1);
-      sb.empty_gen[s] = 0;
-    }
+    for (int s = 0; s < Cfg::NB; s++) sb.empty_gen[s] = 0;
+    sb.progress = -1;
     sb.next_q = 0;
   }
   // boundary rings start as zeros: a strip without a left neighbour reads its (unused) ring
