@@ -23,6 +23,7 @@
 #include <string.h>
 
 #include "arms.h"
+#include "ars_machine.h"
 #include "yaps.h"
 
 #define X_EPS 0.00001 /* a new point is kept this (relative) distance away from its neighbours */
@@ -35,19 +36,6 @@ typedef struct {
   double cum;  /* integral of the exponentiated envelope up to x */
 } knot_t;
 
-typedef struct {
-  knot_t *k; /* sorted left to right; odd indices are evaluated points */
-  int n, cap;
-  double ymax;
-  double convex;
-  int *neval;
-  double (*f)(double, void *);
-  void *fdata;
-  /* Metropolis state */
-  int metro;
-  double xprev, yprev;
-} env_t;
-
 /* the sampled (not yet incorporated) point: lies on the piece (right-1, right) */
 typedef struct {
   double x, y, ey;
@@ -55,17 +43,44 @@ typedef struct {
   int evaluated;
 } trial_t;
 
+/*
+ * The sampler is a RESUMABLE machine: it runs until it needs the log-density at a point, hands
+ * the point out (ARS_NEED) and continues when the value is fed back.  The scalar entry points
+ * below drive it with the caller's callback; the batched samplers (psample_batch.c) drive
+ * thousands of machines in lock-step and evaluate each round's points in one device batch.
+ * One code path for the arithmetic either way.
+ */
+enum { W_INIT = 0, W_YPREV, W_TRIAL, W_ADJUST, W_IDLE };
+
+struct stb_ars {
+  knot_t *k; /* sorted left to right; odd indices are evaluated points */
+  int n, cap;
+  double ymax;
+  double convex;
+  int neval;
+  int metro;
+  double xprev, yprev;
+  double (*unif)(void *);
+  void *ustate;
+  /* progress */
+  int waiting;  /* what the value being waited for is */
+  int init_i, ninit;
+  trial_t p;
+  double u_y;   /* the rejection threshold log(u * envelope) of the current trial */
+  int iq;       /* index of the point being incorporated */
+  int tries, got, nsamp;
+  double *xsamp;
+  double xl, xr;
+};
+
 double expshift(double y, double y0) { /* exponentiate y shifted by y0 without overflow */
   return (y - y0 > -2.0 * YCEIL) ? exp(y - y0 + YCEIL) : 0.0;
 }
 static double log_unshift(double ey, double y0) { return log(ey) + y0 - YCEIL; }
 
-static double uniform01(void) { return ((double)rand() + 0.5) / 2147483648.0; }
-
-static double density(env_t *e, double x) {
-  const double y = e->f(x, e->fdata);
-  ++*e->neval;
-  return y;
+static double uniform_rand(void *unused) {
+  (void)unused;
+  return ((double)rand() + 0.5) / 2147483648.0;
 }
 
 /*
@@ -73,7 +88,7 @@ static double density(env_t *e, double x) {
  * points on its two sides meet.  Returns 1 when the log-density is found non-concave and no
  * Metropolis step is available to pay for it.
  */
-static int place_intersection(env_t *e, int j) {
+static int place_intersection(stb_ars_t *e, int j) {
   knot_t *k = e->k;
   const int has_l = j >= 3, has_r = j + 3 <= e->n - 1, has_across = j >= 1 && j + 1 <= e->n - 1;
   double gl = 0, gr = 0, gacross = 0, dl = 0, dr = 0;
@@ -118,7 +133,7 @@ static int place_intersection(env_t *e, int j) {
 }
 
 /* exponentiate the envelope (shifted by its maximum) and integrate it piece by piece */
-static void integrate(env_t *e) {
+static void integrate(stb_ars_t *e) {
   knot_t *k = e->k;
   int j;
   e->ymax = k[0].y;
@@ -139,7 +154,7 @@ static void integrate(env_t *e) {
 }
 
 /* the point of the envelope at cumulative probability prob */
-static void invert_cdf(env_t *e, double prob, trial_t *p) {
+static void invert_cdf(stb_ars_t *e, double prob, trial_t *p) {
   const knot_t *k = e->k;
   double xl = 0, xr = 0;
   int r = e->n - 1;
@@ -175,63 +190,103 @@ static void invert_cdf(env_t *e, double prob, trial_t *p) {
   if (p->x < xl || p->x > xr) yaps_quit("ars: sampled point outside its piece (imprecision)\n");
 }
 
+/* ---- the machine ------------------------------------------------------------------------------ */
+#define ARS_NEED STB_ARS_NEED
+#define ARS_DONE STB_ARS_DONE
+#define ARS_GO_ON (-100) /* internal: the proposal is settled, carry on */
+enum { IQ_FULL = -1, IQ_METROPOLIS = -2 }; /* e->iq when no point is being incorporated */
+
 /*
- * Incorporate the evaluated trial point: two new knots (the point and one more intersection),
- * then the four intersections its chords touch are re-placed and the envelope re-integrated.
+ * Second half of incorporating the evaluated trial point (after its position was possibly moved
+ * off its neighbours and re-evaluated): re-place the four intersections its chords touch,
+ * re-integrate, then the rejection test.  Returns 1 accept, 0 reject, -1 envelope violation.
  */
-static int incorporate(env_t *e, const trial_t *p) {
-  knot_t *k = e->k;
-  int at = p->right, iq, lo, hi;
-  if (!p->evaluated || e->n > e->cap - 2) return 0; /* no room: ignore the point */
-  memmove(k + at + 2, k + at, (size_t)(e->n - at) * sizeof *k);
-  e->n += 2;
-  /* the piece's left end is an evaluated point (odd index): new intersection first, then the point */
-  iq = ((at - 1) & 1) ? at + 1 : at;
-  k[iq].x = p->x;
-  k[iq].y = p->y;
-  /* keep the new point off its neighbours (the evaluated points two knots away, or the bounds) */
-  lo = iq - 2 >= 0 ? iq - 2 : iq - 1;
-  hi = iq + 2 <= e->n - 1 ? iq + 2 : iq + 1;
-  if (k[iq].x < (1. - X_EPS) * k[lo].x + X_EPS * k[hi].x) {
-    k[iq].x = (1. - X_EPS) * k[lo].x + X_EPS * k[hi].x;
-    k[iq].y = density(e, k[iq].x);
-  } else if (k[iq].x > X_EPS * k[lo].x + (1. - X_EPS) * k[hi].x) {
-    k[iq].x = X_EPS * k[lo].x + (1. - X_EPS) * k[hi].x;
-    k[iq].y = density(e, k[iq].x);
-  }
-  if (place_intersection(e, iq - 1)) return 1;
-  if (place_intersection(e, iq + 1)) return 1;
-  if (iq - 2 >= 0 && place_intersection(e, iq - 3)) return 1;
-  if (iq + 2 <= e->n - 1 && place_intersection(e, iq + 3)) return 1;
+static int incorporate_finish(stb_ars_t *e) {
+  const int iq = e->iq;
+  if (place_intersection(e, iq - 1)) return -1;
+  if (place_intersection(e, iq + 1)) return -1;
+  if (iq - 2 >= 0 && place_intersection(e, iq - 3)) return -1;
+  if (iq + 2 <= e->n - 1 && place_intersection(e, iq + 3)) return -1;
   integrate(e);
-  return 0;
+  return e->u_y >= e->p.y ? 0 : 1;
 }
 
-/* rejection, squeezing and Metropolis tests: 1 accept, 0 reject, -1 envelope violation */
-static int accept_trial(env_t *e, trial_t *p) {
-  const knot_t *k = e->k;
-  const int r = p->right;
-  double u = uniform01() * p->ey;
-  const double y = log_unshift(u, e->ymax);
-  double ynew;
-  if (!e->metro && r - 2 >= 0 && r + 1 <= e->n - 1) { /* both ends of the piece have a neighbour beyond */
-    const int sl = ((r - 1) & 1) ? r - 1 : r - 2, sr = (r & 1) ? r : r + 1; /* evaluated points around */
-    const double ysq = (k[sr].y * (p->x - k[sl].x) + k[sl].y * (k[sr].x - p->x)) / (k[sr].x - k[sl].x);
-    if (y <= ysq) return 1;
+/* one proposal settled: count it; returns ARS_DONE, an error code, or ARS_GO_ON */
+static int proposal_outcome(stb_ars_t *e, int verdict) {
+  if (verdict == 1)
+    e->xsamp[e->got++] = e->p.x;
+  else if (verdict != 0)
+    return 2000;
+  if (++e->tries > 100) return 2001; /* the reference gives up after 100 proposals (lib/arms.c:227-233) */
+  return e->got < e->nsamp ? ARS_GO_ON : ARS_DONE;
+}
+
+/* run proposals until a log-density value is needed or sampling ends */
+static int run_proposals(stb_ars_t *e, double *x_out) {
+  for (;;) {
+    const knot_t *k;
+    trial_t *p = &e->p;
+    int r, rc;
+    invert_cdf(e, e->unif(e->ustate), p);
+    k = e->k;
+    r = p->right;
+    e->u_y = log_unshift(e->unif(e->ustate) * p->ey, e->ymax);
+    if (!e->metro && r - 2 >= 0 && r + 1 <= e->n - 1) { /* both ends of the piece have a neighbour beyond */
+      const int sl = ((r - 1) & 1) ? r - 1 : r - 2, sr = (r & 1) ? r : r + 1; /* evaluated points around */
+      const double ysq = (k[sr].y * (p->x - k[sl].x) + k[sl].y * (k[sr].x - p->x)) / (k[sr].x - k[sl].x);
+      if (e->u_y <= ysq) { /* accepted by the squeeze: no evaluation */
+        rc = proposal_outcome(e, 1);
+        if (rc != ARS_GO_ON) return rc;
+        continue;
+      }
+    }
+    e->waiting = W_TRIAL;
+    *x_out = p->x;
+    return ARS_NEED;
   }
-  ynew = density(e, p->x);
-  if (!e->metro || y >= ynew) {
+}
+
+/* the value of the trial point has arrived */
+static int trial_value(stb_ars_t *e, double ynew, double *x_out) {
+  trial_t *p = &e->p;
+  knot_t *k = e->k;
+  if (!e->metro || e->u_y >= ynew) {
+    int at = p->right, iq, lo, hi;
     p->y = ynew;
     p->ey = expshift(p->y, e->ymax);
     p->evaluated = 1;
-    if (incorporate(e, p)) return -1;
-    return y >= ynew ? 0 : 1;
+    if (e->n > e->cap - 2) { /* no room in the envelope: the point is not incorporated */
+      e->iq = IQ_FULL;
+      return ARS_GO_ON;
+    }
+    /* two new knots: the point and one more intersection */
+    memmove(k + at + 2, k + at, (size_t)(e->n - at) * sizeof *k);
+    e->n += 2;
+    /* the piece's left end is an evaluated point (odd index): new intersection first, then the point */
+    iq = ((at - 1) & 1) ? at + 1 : at;
+    e->iq = iq;
+    k[iq].x = p->x;
+    k[iq].y = p->y;
+    /* keep the new point off its neighbours (the evaluated points two knots away, or the bounds) */
+    lo = iq - 2 >= 0 ? iq - 2 : iq - 1;
+    hi = iq + 2 <= e->n - 1 ? iq + 2 : iq + 1;
+    if (k[iq].x < (1. - X_EPS) * k[lo].x + X_EPS * k[hi].x) {
+      k[iq].x = (1. - X_EPS) * k[lo].x + X_EPS * k[hi].x;
+      e->waiting = W_ADJUST;
+      *x_out = k[iq].x;
+      return ARS_NEED;
+    } else if (k[iq].x > X_EPS * k[lo].x + (1. - X_EPS) * k[hi].x) {
+      k[iq].x = X_EPS * k[lo].x + (1. - X_EPS) * k[hi].x;
+      e->waiting = W_ADJUST;
+      *x_out = k[iq].x;
+      return ARS_NEED;
+    }
+    return ARS_GO_ON;
   }
   /* Metropolis step against the previous iterate */
   {
     int l = 0;
-    double w, zold, znew, yold = e->yprev;
-    k = e->k;
+    double w, zold, znew, yold = e->yprev, u;
     while (k[l + 1].x < e->xprev) l++;
     w = (e->xprev - k[l].x) / (k[l + 1].x - k[l].x);
     zold = k[l].y + w * (k[l + 1].y - k[l].y);
@@ -241,7 +296,7 @@ static int accept_trial(env_t *e, trial_t *p) {
     w = ynew - znew - yold + zold;
     if (w > 0.0) w = 0.0;
     w = (w > -YCEIL) ? exp(w) : 0.0;
-    u = uniform01();
+    u = e->unif(e->ustate);
     if (u > w) { /* stay */
       p->x = e->xprev;
       p->y = e->yprev;
@@ -253,78 +308,146 @@ static int accept_trial(env_t *e, trial_t *p) {
       e->yprev = ynew;
     }
   }
-  return 1;
+  e->iq = IQ_METROPOLIS; /* settled by the Metropolis step: accepted */
+  return ARS_GO_ON;
 }
 
+stb_ars_t *stb_ars_new(int npoint) {
+  stb_ars_t *e = (stb_ars_t *)calloc(1, sizeof *e);
+  if (!e) return NULL;
+  e->k = (knot_t *)malloc((size_t)(npoint > 0 ? npoint : 1) * sizeof(knot_t));
+  if (!e->k) {
+    free(e);
+    return NULL;
+  }
+  e->cap = npoint;
+  return e;
+}
+
+void stb_ars_free(stb_ars_t *e) {
+  if (!e) return;
+  free(e->k);
+  free(e);
+}
+
+int stb_ars_neval(const stb_ars_t *e) { return e->neval; }
+
+/*
+ * Start sampling nsamp points.  Argument checks as the reference makes them, in its order
+ * (lib/arms.c:286-318).  Returns ARS_NEED with the first point to evaluate in *x_out, or a code.
+ */
+int stb_ars_begin(stb_ars_t *e, const double *xinit, int ninit, double xl, double xr, double convex, int dometrop,
+                  double xprev, double *xsamp, int nsamp, double (*unif)(void *), void *ustate, double *x_out) {
+  int i;
+  const int n0 = 2 * ninit + 1;
+  if (ninit < 3) return 1001;
+  if (e->cap < n0) return 1002;
+  if (xinit[0] <= xl || xinit[ninit - 1] >= xr) return 1003;
+  for (i = 1; i < ninit; i++)
+    if (xinit[i] <= xinit[i - 1]) return 1004;
+  if (convex < 0.0) return 1008;
+  e->n = n0;
+  e->convex = convex;
+  e->neval = 0;
+  e->metro = dometrop;
+  e->xprev = xprev;
+  e->unif = unif ? unif : uniform_rand;
+  e->ustate = ustate;
+  e->xl = xl;
+  e->xr = xr;
+  e->xsamp = xsamp;
+  e->nsamp = nsamp;
+  e->got = e->tries = 0;
+  memset(e->k, 0, (size_t)e->cap * sizeof(knot_t));
+  e->k[0].x = xl;
+  e->k[n0 - 1].x = xr;
+  for (i = 0; i < ninit; i++) e->k[2 * i + 1].x = xinit[i];
+  e->ninit = ninit;
+  e->init_i = 0;
+  e->waiting = W_INIT;
+  *x_out = xinit[0];
+  return ARS_NEED;
+}
+
+/* feed the log-density at the point last handed out; returns ARS_NEED (next point in *x_out), ARS_DONE or a code */
+int stb_ars_feed(stb_ars_t *e, double y, double *x_out) {
+  int rc, verdict;
+  e->neval++;
+  switch (e->waiting) {
+    case W_INIT:
+      e->k[2 * e->init_i + 1].y = y;
+      if (++e->init_i < e->ninit) {
+        *x_out = e->k[2 * e->init_i + 1].x;
+        return ARS_NEED;
+      }
+      for (int j = 0; j < e->n; j += 2)
+        if (place_intersection(e, j)) return 2000;
+      integrate(e);
+      if (e->metro) {
+        if (e->xprev < e->xl || e->xprev > e->xr) {
+          e->xsamp[0] = e->xprev < e->xl ? e->xl : e->xr;
+          return 1007;
+        }
+        e->waiting = W_YPREV;
+        *x_out = e->xprev;
+        return ARS_NEED;
+      }
+      return run_proposals(e, x_out);
+    case W_YPREV:
+      e->yprev = y;
+      return run_proposals(e, x_out);
+    case W_TRIAL:
+      rc = trial_value(e, y, x_out);
+      if (rc == ARS_NEED) return rc;
+      if (e->iq == IQ_METROPOLIS)
+        verdict = 1;
+      else if (e->iq == IQ_FULL)
+        verdict = e->u_y >= e->p.y ? 0 : 1; /* envelope full: plain rejection test */
+      else
+        verdict = incorporate_finish(e);
+      break;
+    case W_ADJUST:
+      e->k[e->iq].y = y;
+      verdict = incorporate_finish(e);
+      break;
+    default:
+      return 2002;
+  }
+  e->waiting = W_IDLE;
+  rc = proposal_outcome(e, verdict);
+  if (rc != ARS_GO_ON) return rc;
+  return run_proposals(e, x_out);
+}
+
+/* envelope centile (after ARS_DONE) */
+double stb_ars_centile(stb_ars_t *e, double q) {
+  trial_t p;
+  invert_cdf(e, q / 100.0, &p);
+  return p.x;
+}
+
+/* ---- the reference's entry points: the machine driven by the caller's callback ----------------- */
 int arms(double *xinit, int ninit, double *xl, double *xr, double (*myfunc)(double x, void *mydata), void *mydata,
          double *convex, int npoint, int dometrop, double *xprev, double *xsamp, int nsamp, double *qcent,
          double *xcent, int ncent, int *neval) {
-  env_t e;
-  trial_t p;
-  int i, j, got = 0, tries = 0, n0;
+  stb_ars_t *e;
+  double x = 0;
+  int i, rc;
   for (i = 0; i < ncent; i++)
     if (qcent[i] < 0.0 || qcent[i] > 100.0) return 1005;
-  /* the reference's argument checks, in its order (lib/arms.c:286-318) */
+  /* (the reference checks ninit and npoint before it allocates, lib/arms.c:286-296) */
   if (ninit < 3) return 1001;
-  n0 = 2 * ninit + 1;
-  if (npoint < n0) return 1002;
-  if (xinit[0] <= *xl || xinit[ninit - 1] >= *xr) return 1003;
-  for (i = 1; i < ninit; i++)
-    if (xinit[i] <= xinit[i - 1]) return 1004;
-  if (*convex < 0.0) return 1008;
-  memset(&e, 0, sizeof e);
-  e.k = (knot_t *)malloc((size_t)npoint * sizeof(knot_t));
-  if (!e.k) return 1006;
-  e.cap = npoint;
-  e.n = n0;
-  e.convex = *convex;
-  e.neval = neval;
+  if (npoint < 2 * ninit + 1) return 1002;
+  e = stb_ars_new(npoint);
+  if (!e) return 1006;
   *neval = 0;
-  e.f = myfunc;
-  e.fdata = mydata;
-  e.metro = dometrop;
-  memset(e.k, 0, (size_t)npoint * sizeof(knot_t));
-  e.k[0].x = *xl;
-  e.k[n0 - 1].x = *xr;
-  for (i = 0; i < ninit; i++) {
-    e.k[2 * i + 1].x = xinit[i];
-    e.k[2 * i + 1].y = density(&e, xinit[i]);
-  }
-  for (j = 0; j < n0; j += 2)
-    if (place_intersection(&e, j)) {
-      free(e.k);
-      return 2000;
-    }
-  integrate(&e);
-  if (dometrop) {
-    if (*xprev < *xl || *xprev > *xr) {
-      *xsamp = *xprev < *xl ? *xl : *xr;
-      free(e.k);
-      return 1007;
-    }
-    e.xprev = *xprev;
-    e.yprev = density(&e, *xprev);
-  }
-  do {
-    invert_cdf(&e, uniform01(), &p);
-    i = accept_trial(&e, &p);
-    if (i == 1)
-      xsamp[got++] = p.x;
-    else if (i != 0) {
-      free(e.k);
-      return 2000;
-    }
-    if (++tries > 100) { /* the reference gives up after 100 proposals (lib/arms.c:227-233) */
-      free(e.k);
-      return 2001;
-    }
-  } while (got < nsamp);
-  for (i = 0; i < ncent; i++) {
-    invert_cdf(&e, qcent[i] / 100.0, &p);
-    xcent[i] = p.x;
-  }
-  free(e.k);
-  return 0;
+  rc = stb_ars_begin(e, xinit, ninit, *xl, *xr, *convex, dometrop, *xprev, xsamp, nsamp, NULL, NULL, &x);
+  while (rc == ARS_NEED) rc = stb_ars_feed(e, myfunc(x, mydata), &x);
+  *neval = e->neval;
+  if (rc == ARS_DONE)
+    for (i = 0; i < ncent; i++) xcent[i] = stb_ars_centile(e, qcent[i]);
+  stb_ars_free(e);
+  return rc;
 }
 
 int arms_simple(int ninit, double *xl, double *xr, double (*myfunc)(double x, void *mydata), void *mydata,
