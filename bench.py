@@ -291,6 +291,38 @@ def run_extras():
         res["cpu_reference"] = {"samples_per_s": 6 / (time.perf_counter() - t0), "cores": 1, "chains": 3,
                                 "a_draws_match": bool(ok)}
     out["config4_samplers"] = res
+    # --- the same in the reference's DEFAULT (ARS) configuration: batched arms_simple machines ---
+    rnd0 = stb.rand31_states([777 + c for c in range(Cn)])
+    stb.samplea_batch_ars(a0[:64], cts, bpar, rnd0[:64])  # warm-up
+    t0 = time.perf_counter()
+    a2, rnd1, sa2 = stb.samplea_batch_ars(a0, cts, bpar, rnd0)
+    b2, _, _, sb2 = stb.sampleb_batch_ars(np.full(Cn, 10.0), cts, 1.1, 20.0, a2, r0, rnd1)
+    wall = time.perf_counter() - t0
+    res2 = {"chains": Cn, "samples_per_s": 2 * Cn / wall, "wall_s": wall, "a_evals": int(sa2["evals"]),
+            "a_rounds": int(sa2["rounds"]), "a_device_ms": sa2["eval_ms"], "b_evals": int(sb2["evals"]),
+            "in_bounds": bool(((a2 >= 0.01) & (a2 <= 0.98) & (b2 >= 0.01) & (b2 <= 2000)).all())}
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libstb_ref.so")
+    if os.path.exists(ref_so):  # the reference's default build on one host core, three chains
+        R = C.CDLL(ref_so)
+        d, u32p = C.c_double, C.POINTER(C.c_uint32)
+        R.samplea.restype = d
+        R.samplea.argtypes = [d, C.c_int, C.POINTER(C.c_int), u32p, C.POINTER(u32p), C.POINTER(C.POINTER(C.c_uint16)),
+                              C.c_void_p, C.POINTER(d), C.c_void_p, C.c_int, C.c_int]
+        R.sampleb.restype, R.sampleb.argtypes = d, [d, C.c_int, d, d, u32p, u32p, d, C.c_void_p, C.c_int, C.c_int]
+        libc = C.CDLL(None)
+        libc.srand.argtypes = [C.c_uint]
+        libc.srand48.argtypes = [C.c_long]
+        t0 = time.perf_counter()
+        ok = True
+        for c in range(3):
+            libc.srand(777 + c)
+            libc.srand48(12345 + c)
+            ar = R.samplea(float(a0[c]), *cts.args(), None, bpar.ctypes.data_as(C.POINTER(d)), None, 1, 0)
+            R.sampleb(10.0, cts.I, 1.1, 20.0, cts.N.ctypes.data_as(u32p), cts.T.ctypes.data_as(u32p), ar, None, 1, 0)
+            ok = ok and abs(ar - a2[c]) <= 1e-9 * abs(ar)
+        res2["cpu_reference"] = {"samples_per_s": 6 / (time.perf_counter() - t0), "cores": 1, "chains": 3,
+                                 "a_draws_match": bool(ok)}
+    out["config4_samplers_ars"] = res2
     # --- config 2 in the other storage modes (S-only, V-only, S+V, FP64 and S_FLOAT) ---
     S, V, F = stb.S_STABLE, stb.S_UVTABLE, stb.S_FLOAT
     cS, cV = cells_S(N_ROWS, M_COLS), M_COLS * (M_COLS - 1) // 2 + (N_ROWS - M_COLS) * (M_COLS - 1)

@@ -106,6 +106,21 @@ int stb_samplea_batch(double *a, size_t C, int I, const int *K, const scnt_int *
 int stb_sampleb_batch(double *b, size_t C, int I, double shape, double scale, const scnt_int *N, const scnt_int *T,
                       const double *apar, uint64_t *rng, int loops, stb_sample_stats *st);
 
+/*
+ * The same in the reference's DEFAULT (ARS) configuration: every chain runs arms_simple(3, ...)
+ * (lib/samplea.c:209-215 on [a - SQUEEZEA, a + SQUEEZEA] clipped to [A_MIN, A_MAX];
+ * lib/sampleb.c:127-140 on [B_MIN, B_MAX]) as a resumable machine, the chains advance in lock-step
+ * and each round's log-posterior evaluations are one device batch.  rnd[c]: the chain's rand()
+ * stream (stb_rand31_t, include/stb_b200.h), in/out; rng[c] (sampleb): its 48-bit stream for the
+ * auxiliary Beta draws.  Returns 0, or 1 + the index of the first failing chain.
+ */
+struct stb_rand31;
+int stb_samplea_batch_ars(double *a, size_t C, int I, const int *K, const scnt_int *T, scnt_int **n, stcnt_int **t,
+                          const double *bpar, int bpar_per_chain, struct stb_rand31 *rnd, stb_sample_stats *st);
+int stb_sampleb_batch_ars(double *b, size_t C, int I, double shape, double scale, const scnt_int *N,
+                          const scnt_int *T, const double *apar, uint64_t *rng, struct stb_rand31 *rnd,
+                          stb_sample_stats *st);
+
 #ifdef __cplusplus
 }
 #endif

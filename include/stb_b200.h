@@ -66,6 +66,19 @@ double stb_sweep_last_fill_ms(const stb_sweep_t *w);
 int stb_sweep_tables_in_flight(const stb_sweep_t *w);
 void stb_sweep_free(stb_sweep_t *w);
 
+/*
+ * Per-chain replacement for the C library's rand() / srand() (glibc's additive feedback generator,
+ * csrc/rand31.h): stb_rand31_seed(g, s) puts g in the state srand(s) puts the global generator in,
+ * stb_rand31_next(g) returns what rand() would return next.  The batched ARS samplers draw each
+ * chain's uniforms from its own stb_rand31_t (the reference's ARMS uses rand(), lib/arms.c:913-918).
+ */
+typedef struct stb_rand31 {
+  int32_t r[31];
+  int32_t f, b;
+} stb_rand31_t;
+void stb_rand31_seed(stb_rand31_t *g, unsigned seed);
+int stb_rand31_next(stb_rand31_t *g);
+
 /* frees device memory the batched samplers keep between calls (the sweep handle of the last
  * stb_samplea_batch: one launch's worth of table slabs) */
 void stb_release_caches(void);

@@ -95,6 +95,13 @@ def lib() -> C.CDLL:
     L.stb_rng48_gaussian.restype, L.stb_rng48_gaussian.argtypes = d, [u64p, d]
     L.stb_rng48_gamma.restype, L.stb_rng48_gamma.argtypes = d, [u64p, d]
     L.stb_rng48_beta.restype, L.stb_rng48_beta.argtypes = d, [u64p, d, d]
+    L.stb_rand31_seed.restype, L.stb_rand31_seed.argtypes = None, [vp, C.c_uint]
+    L.stb_rand31_next.restype, L.stb_rand31_next.argtypes = C.c_int, [vp]
+    L.stb_samplea_batch_ars.restype = C.c_int
+    L.stb_samplea_batch_ars.argtypes = [dp, C.c_size_t, C.c_int, ip, u32p, C.POINTER(u32p),
+                                        C.POINTER(C.POINTER(C.c_uint16)), dp, C.c_int, vp, vp]
+    L.stb_sampleb_batch_ars.restype = C.c_int
+    L.stb_sampleb_batch_ars.argtypes = [dp, C.c_size_t, C.c_int, d, d, u32p, u32p, dp, u64p, vp, vp]
     L.stb_samplea_batch.restype = C.c_int
     L.stb_samplea_batch.argtypes = [dp, C.c_size_t, C.c_int, ip, u32p, C.POINTER(u32p),
                                     C.POINTER(C.POINTER(C.c_uint16)), dp, C.c_int, u64p, C.c_int, vp]
@@ -309,3 +316,47 @@ def sampleb_batch(b, counts, shape, scale, apar, rng, loops=1, trace_cap=0):
     if rc:
         raise RuntimeError(f"stb_sampleb_batch failed ({rc}): " + L.stb_last_error().decode())
     return b, rng, {"evals": st.evals, "rounds": st.rounds, "eval_ms": st.eval_ms, "trace": keep}
+
+
+RAND31_DTYPE = np.dtype([("r", np.int32, 31), ("f", np.int32), ("b", np.int32)])  # stb_rand31_t
+
+
+def rand31_states(seeds):
+    """per-chain rand() streams: element c is in the state srand(seeds[c]) puts glibc's generator in"""
+    L = lib()
+    g = np.zeros(len(seeds), dtype=RAND31_DTYPE)
+    for c, s in enumerate(seeds):
+        L.stb_rand31_seed(g.ctypes.data + c * RAND31_DTYPE.itemsize, int(s))
+    return g
+
+
+def samplea_batch_ars(a, counts, bpar, rnd, bpar_per_chain=False, trace_cap=0):
+    """stb_samplea_batch_ars: returns (a_new, rnd_new, stats dict)."""
+    L = lib()
+    a = np.array(a, dtype=np.float64)
+    rnd = np.array(rnd, dtype=RAND31_DTYPE)
+    bpar = np.ascontiguousarray(bpar, dtype=np.float64)
+    st, keep = _stats(a.shape[0], trace_cap)
+    dp = C.POINTER(C.c_double)
+    rc = L.stb_samplea_batch_ars(a.ctypes.data_as(dp), a.shape[0], *counts.args(), bpar.ctypes.data_as(dp),
+                                 int(bpar_per_chain), rnd.ctypes.data, C.byref(st))
+    if rc:
+        raise RuntimeError(f"stb_samplea_batch_ars failed ({rc}): " + L.stb_last_error().decode())
+    return a, rnd, {"evals": st.evals, "rounds": st.rounds, "eval_ms": st.eval_ms, "trace": keep}
+
+
+def sampleb_batch_ars(b, counts, shape, scale, apar, rng, rnd, trace_cap=0):
+    """stb_sampleb_batch_ars: returns (b_new, rng_new, rnd_new, stats dict)."""
+    L = lib()
+    b = np.array(b, dtype=np.float64)
+    rng = np.array(rng, dtype=np.uint64)
+    rnd = np.array(rnd, dtype=RAND31_DTYPE)
+    apar = np.ascontiguousarray(apar, dtype=np.float64)
+    st, keep = _stats(b.shape[0], trace_cap)
+    dp, u64p, u32p = C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
+    rc = L.stb_sampleb_batch_ars(b.ctypes.data_as(dp), b.shape[0], counts.I, shape, scale,
+                                 counts.N.ctypes.data_as(u32p), counts.T.ctypes.data_as(u32p), apar.ctypes.data_as(dp),
+                                 rng.ctypes.data_as(u64p), rnd.ctypes.data, C.byref(st))
+    if rc:
+        raise RuntimeError(f"stb_sampleb_batch_ars failed ({rc}): " + L.stb_last_error().decode())
+    return b, rng, rnd, {"evals": st.evals, "rounds": st.rounds, "eval_ms": st.eval_ms, "trace": keep}

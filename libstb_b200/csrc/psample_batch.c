@@ -15,7 +15,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "ars_machine.h"
 #include "psample.h"
+#include "rand31.h"
 #include "rng48.h"
 #include "specfun.h"
 #include "stb_b200.h"
@@ -179,6 +181,81 @@ done:
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* lock-step adaptive rejection sampler                                                        */
+/* ------------------------------------------------------------------------------------------ */
+void stb_rand31_seed(stb_rand31_t *g, unsigned seed) { stb_rand31_init(g, seed); }
+int stb_rand31_next(stb_rand31_t *g) { return stb_rand31_step(g); }
+
+/*
+ * One arms_simple(3, lo, hi, ...) per chain (envelope of at most 100 knots, no Metropolis step:
+ * lib/arms.c:98-123 as samplea / sampleb call it), every chain a resumable machine on its own
+ * rand() stream.  Each round evaluates the one point every unfinished chain is waiting for.
+ * xp[c] receives the draw.  Returns 0, -1/-2 (memory / evaluation failure), or 1 + the index of
+ * the first chain whose sampler reported an error (its arms() code goes to stderr).
+ */
+static int ars_lockstep(double *xp, size_t C, const double *lo, const double *hi, stb_rand31_t *rnd, eval_fn eval,
+                        void *ctx, stb_sample_stats *st) {
+  stb_ars_t **m = (stb_ars_t **)calloc(C, sizeof *m);
+  int *state = (int *)malloc(sizeof(int) * C), *chain = (int *)malloc(sizeof(int) * C);
+  double *want = (double *)malloc(sizeof(double) * C), *xq = (double *)malloc(sizeof(double) * C);
+  double *val = (double *)malloc(sizeof(double) * C);
+  size_t c, cnt;
+  int rc = 0;
+  if (!m || !state || !chain || !want || !xq || !val) {
+    rc = -1;
+    goto done;
+  }
+  for (c = 0; c < C; c++) {
+    double xinit[3];
+    int i;
+    m[c] = stb_ars_new(100);
+    if (!m[c]) {
+      rc = -1;
+      goto done;
+    }
+    for (i = 0; i < 3; i++) xinit[i] = lo[c] + (i + 1.0) * (hi[c] - lo[c]) / (3 + 1.0);
+    state[c] = stb_ars_begin(m[c], xinit, 3, lo[c], hi[c], 1.0, 0, 0.0, &xp[c], 1, stb_rand31_unit, &rnd[c], &want[c]);
+  }
+  for (;;) {
+    cnt = 0;
+    for (c = 0; c < C; c++) {
+      if (state[c] == STB_ARS_NEED) {
+        xq[cnt] = want[c];
+        chain[cnt++] = (int)c;
+      } else if (state[c] != STB_ARS_DONE) {
+        fprintf(stderr, "arms_simple: error %d (chain %zu, bounds [%lg,%lg])\n", state[c], c, lo[c], hi[c]);
+        rc = 1 + (int)c;
+        goto done;
+      }
+    }
+    if (!cnt) break;
+    if (eval(ctx, xq, chain, cnt, val)) {
+      rc = -2;
+      goto done;
+    }
+    if (st) {
+      st->evals += cnt;
+      st->rounds++;
+    }
+    for (size_t j = 0; j < cnt; j++) {
+      c = (size_t)chain[j];
+      trace_add(st, c, xq[j], val[j]);
+      state[c] = stb_ars_feed(m[c], val[j], &want[c]);
+    }
+  }
+done:
+  if (m)
+    for (c = 0; c < C; c++) stb_ars_free(m[c]);
+  free(m);
+  free(state);
+  free(chain);
+  free(want);
+  free(xq);
+  free(val);
+  return rc;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* samplea, batched                                                                            */
 /* ------------------------------------------------------------------------------------------ */
 typedef struct {
@@ -239,8 +316,9 @@ static void sweep_release(stb_sweep_t *w, unsigned N, unsigned M) {
   g_sweep_cache.M = M;
 }
 
-int stb_samplea_batch(double *a, size_t C, int I, const int *K, const scnt_int *T, scnt_int **n, stcnt_int **t,
-                      const double *bpar, int bpar_per_chain, uint64_t *rng, int loops, stb_sample_stats *st) {
+static int samplea_batch_core(double *a, size_t C, int I, const int *K, const scnt_int *T, scnt_int **n,
+                              stcnt_int **t, const double *bpar, int bpar_per_chain, uint64_t *rng,
+                              stb_rand31_t *rnd, int loops, stb_sample_stats *st) {
   double *lo = NULL, *hi = NULL;
   uint32_t *nn = NULL, *tt = NULL;
   size_t total = 0, cnt = 0, c;
@@ -263,7 +341,8 @@ int stb_samplea_batch(double *a, size_t C, int I, const int *K, const scnt_int *
     if (fabs(mid - A_MAX) / A_MAX < 0.00001) mid = A_MAX * 0.999 + A_MIN * 0.001;
     if (fabs(mid - A_MIN) / A_MIN < 0.00001) mid = A_MIN * 0.999 + A_MAX * 0.001;
     lo[c] = (mid - SQUEEZEA > A_MIN) ? mid - SQUEEZEA : A_MIN;
-    hi[c] = A_MAX;
+    /* the slice sampler may move up to A_MAX (lib/samplea.c:217); ARS stays inside the squeeze (:176-177) */
+    hi[c] = (rnd && mid + SQUEEZEA < A_MAX) ? mid + SQUEEZEA : A_MAX;
   }
   /* the statistics with n > 1 in (i,k) order; table extent as lib/samplea.c:186-208 */
   for (i = 0; i < I; i++)
@@ -287,7 +366,15 @@ int stb_samplea_batch(double *a, size_t C, int I, const int *K, const scnt_int *
   if (!ab.ps) goto done;
   ab.bpar_per_chain = bpar_per_chain;
   ab.st = st;
-  rc = slice_lockstep(a, C, lo, hi, rng, loops, aterms_batch, &ab, st);
+  if (rnd) {
+    rc = ars_lockstep(a, C, lo, hi, rnd, aterms_batch, &ab, st);
+    for (c = 0; rc == 0 && c < C; c++)
+      if (a[c] < lo[c] || a[c] > hi[c]) {
+        fprintf(stderr, "Arms_simple(apar) returned value out of bounds (chain %zu)\n", c);
+        rc = 1 + (int)c;
+      }
+  } else
+    rc = slice_lockstep(a, C, lo, hi, rng, loops, aterms_batch, &ab, st);
 done:
   if (ab.sweep) sweep_release(ab.sweep, Nx, Mx);
   if (ab.ps) stb_cuda_pstat_destroy(ab.ps);
@@ -298,6 +385,17 @@ done:
   free(ab.ssum);
   free(ab.lg);
   return rc;
+}
+
+int stb_samplea_batch(double *a, size_t C, int I, const int *K, const scnt_int *T, scnt_int **n, stcnt_int **t,
+                      const double *bpar, int bpar_per_chain, uint64_t *rng, int loops, stb_sample_stats *st) {
+  return samplea_batch_core(a, C, I, K, T, n, t, bpar, bpar_per_chain, rng, NULL, loops, st);
+}
+
+int stb_samplea_batch_ars(double *a, size_t C, int I, const int *K, const scnt_int *T, scnt_int **n, stcnt_int **t,
+                          const double *bpar, int bpar_per_chain, stb_rand31_t *rnd, stb_sample_stats *st) {
+  if (!rnd) return -1;
+  return samplea_batch_core(a, C, I, K, T, n, t, bpar, bpar_per_chain, NULL, rnd, 1, st);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -327,8 +425,9 @@ static int bterms_batch(void *ctx, const double *x, const int *chain, size_t cnt
 #define B_ERROR 1.0e-4
 #define B_LOOPS 5
 
-int stb_sampleb_batch(double *b, size_t C, int I, double shape, double scale, const scnt_int *N, const scnt_int *T,
-                      const double *apar, uint64_t *rng, int loops, stb_sample_stats *st) {
+static int sampleb_batch_core(double *b, size_t C, int I, double shape, double scale, const scnt_int *N,
+                              const scnt_int *T, const double *apar, uint64_t *rng, stb_rand31_t *rnd, int loops,
+                              stb_sample_stats *st) {
   double *Q = NULL, *lo = NULL, *hi = NULL, *x = NULL, *xprime = NULL, *dsum = NULL, *xs = NULL, *as = NULL;
   int *idx = NULL, *bl = NULL;
   size_t c, cnt;
@@ -383,10 +482,12 @@ int stb_sampleb_batch(double *b, size_t C, int I, double shape, double scale, co
       b[c] = myb;
     }
   }
-  /* a > 0 chains: bmax warm-up in lock-step (lib/sampleb.c:51-68), then the slice sampler */
+  /* a > 0 chains: bmax warm-up in lock-step (lib/sampleb.c:51-68), then the slice sampler; in the ARS
+   * configuration there is no warm-up (lib/sampleb.c:127-140) */
   for (c = 0; c < C; c++) {
-    bl[c] = B_LOOPS;
-    if (apar[c] != 0) {
+    bl[c] = rnd ? 0 : B_LOOPS;
+    xprime[c] = b[c];
+    if (apar[c] != 0 && !rnd) {
       if (b[c] <= 0) {
         fprintf(stderr, "Illegal concentration value in bmax()\n");
         rc = 1 + (int)c;
@@ -455,7 +556,23 @@ int stb_sampleb_batch(double *b, size_t C, int I, double shape, double scale, co
       sp = &sub;
     }
     bb.st = sp;
-    rc = slice_lockstep(xs, cnt, lo, hi, r2, loops, bterms_batch, &bb, sp);
+    if (rnd) {
+      stb_rand31_t *g2 = (stb_rand31_t *)malloc(sizeof(stb_rand31_t) * cnt);
+      if (!g2)
+        rc = -1;
+      else {
+        for (size_t j = 0; j < cnt; j++) g2[j] = rnd[idx[j]];
+        rc = ars_lockstep(xs, cnt, lo, hi, g2, bterms_batch, &bb, sp);
+        for (size_t j = 0; j < cnt; j++) rnd[idx[j]] = g2[j];
+        for (size_t j = 0; rc == 0 && j < cnt; j++)
+          if (xs[j] < B_MIN || xs[j] > B_MAX) {
+            fprintf(stderr, "Arms_simple(bpar) returned value out of bounds (chain %d)\n", idx[j]);
+            rc = 1 + (int)j;
+          }
+        free(g2);
+      }
+    } else
+      rc = slice_lockstep(xs, cnt, lo, hi, r2, loops, bterms_batch, &bb, sp);
     if (st) {
       st->evals = sub.evals;
       st->rounds = sub.rounds;
@@ -486,4 +603,16 @@ done:
   free(bb.qv);
   free(bb.av);
   return rc;
+}
+
+int stb_sampleb_batch(double *b, size_t C, int I, double shape, double scale, const scnt_int *N, const scnt_int *T,
+                      const double *apar, uint64_t *rng, int loops, stb_sample_stats *st) {
+  return sampleb_batch_core(b, C, I, shape, scale, N, T, apar, rng, NULL, loops, st);
+}
+
+int stb_sampleb_batch_ars(double *b, size_t C, int I, double shape, double scale, const scnt_int *N,
+                          const scnt_int *T, const double *apar, uint64_t *rng, stb_rand31_t *rnd,
+                          stb_sample_stats *st) {
+  if (!rnd) return -1;
+  return sampleb_batch_core(b, C, I, shape, scale, N, T, apar, rng, rnd, 1, st);
 }

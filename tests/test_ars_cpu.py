@@ -158,3 +158,15 @@ def test_arms_simple_distribution():
     xs = np.array([x for rc, x in _simple(stb.lib(), f, xl, xr, 42, 4000) if rc == 0])
     assert len(xs) == 4000
     assert abs(xs.mean() - 0.3) < 0.02 and abs(xs.std() - 0.2) < 0.02
+
+
+def test_rand31_is_glibc_rand():
+    """stb_rand31_t (csrc/rand31.h) reproduces srand()/rand() bit for bit: the per-chain streams of
+    the batched ARS samplers are the streams the reference's global generator would produce"""
+    L = stb.lib()
+    libc.rand.restype = C.c_int
+    for seed in (0, 1, 2, 777, 12345, 2**31 - 1, 2**32 - 5):
+        g = stb.rand31_states([seed])
+        libc.srand(seed)
+        for _ in range(2000):
+            assert L.stb_rand31_next(g.ctypes.data) == libc.rand()

@@ -214,3 +214,59 @@ def test_scalar_samplea_ars_mode_matches_reference_default_build():
             a_our = a_ref
     finally:
         L.stb_set_sampler(old)
+
+
+def _ref_default():
+    R = C.CDLL(harness.REF_SO)  # default build = ARS configuration
+    d, u32p = C.c_double, C.POINTER(C.c_uint32)
+    R.samplea.restype = d
+    R.samplea.argtypes = [d, C.c_int, C.POINTER(C.c_int), u32p, C.POINTER(u32p), C.POINTER(C.POINTER(C.c_uint16)),
+                          C.c_void_p, C.POINTER(d), C.c_void_p, C.c_int, C.c_int]
+    R.sampleb.restype, R.sampleb.argtypes = d, [d, C.c_int, d, d, u32p, u32p, d, C.c_void_p, C.c_int, C.c_int]
+    libc.srand.argtypes = [C.c_uint]
+    libc.rand.restype = C.c_int
+    return R
+
+
+@pytest.mark.skipif(not os.path.exists(harness.REF_SO), reason="reference build not present")
+def test_batched_samplea_ars_matches_reference_chain_by_chain():
+    """stb_samplea_batch_ars: C chains of arms_simple in lock-step, one device batch per round,
+    against the reference's default (ARS) build run chain by chain from the same srand() seeds:
+    draws 1e-9, and every chain's rand() stream ends where the reference's does."""
+    L, R = stb.lib(), _ref_default()
+    cts = _counts(44, I=10, K=12, nmax=300)
+    bpar = np.full(cts.I, 7.0)
+    dp = C.POINTER(C.c_double)
+    Cn = 24
+    a0 = 0.05 + 0.9 * (np.arange(Cn) + 0.5) / Cn
+    seeds = [700 + c for c in range(Cn)]
+    a1, rnd, stats = stb.samplea_batch_ars(a0, cts, bpar, stb.rand31_states(seeds))
+    assert stats["evals"] >= 3 * Cn and stats["rounds"] >= 4
+    for c in range(Cn):
+        libc.srand(seeds[c])
+        a_ref = R.samplea(float(a0[c]), *cts.args(), None, bpar.ctypes.data_as(dp), None, 1, 0)
+        assert a1[c] == pytest.approx(a_ref, rel=1e-9), c
+        assert L.stb_rand31_next(rnd.ctypes.data + c * stb.RAND31_DTYPE.itemsize) == libc.rand(), c
+        assert max(0.01, a0[c] - 0.2) <= a1[c] <= min(0.98, a0[c] + 0.2)
+
+
+@pytest.mark.skipif(not os.path.exists(harness.REF_SO), reason="reference build not present")
+def test_batched_sampleb_ars_matches_reference_chain_by_chain():
+    L, R = stb.lib(), _ref_default()
+    cts = _counts(45, I=60, K=8, nmax=200)
+    u32p = C.POINTER(C.c_uint32)
+    Cn = 20
+    apar = np.where(np.arange(Cn) % 5 == 4, 0.0, 0.1 + 0.8 * np.arange(Cn) / Cn)  # every fifth chain is a DP (a = 0)
+    b0 = np.linspace(0.5, 40.0, Cn)
+    s48 = [300 + c for c in range(Cn)]
+    s31 = [400 + c for c in range(Cn)]
+    r48 = np.array([L.stb_rng48_state(s) for s in s48], dtype=np.uint64)
+    b1, r48b, rnd, stats = stb.sampleb_batch_ars(b0, cts, 1.1, 20.0, apar, r48, stb.rand31_states(s31))
+    for c in range(Cn):
+        libc.srand48(s48[c])
+        libc.srand(s31[c])
+        b_ref = R.sampleb(float(b0[c]), cts.I, 1.1, 20.0, cts.N.ctypes.data_as(u32p), cts.T.ctypes.data_as(u32p),
+                          float(apar[c]), None, 1, 0)
+        assert b1[c] == pytest.approx(b_ref, rel=1e-9), (c, apar[c])
+        assert L.stb_rand31_next(rnd.ctypes.data + c * stb.RAND31_DTYPE.itemsize) == libc.rand(), c
+        assert 0.01 <= b1[c] <= 2000
