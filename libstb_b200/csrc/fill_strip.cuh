@@ -88,6 +88,13 @@ struct StripParams {
   int ctas;  // CTAs per table (= ceil(P / G))
   uint4 *gring;  // [boundaries][ST_NBG*(ST_B+1)] flag-in-data entries, zeroed before each launch
   int *gtaken;   // [boundaries] reader progress (back-pressure only)
+  // Tables wider than one launch can hold are filled in several passes over the columns: a pass
+  // covers strips strip_base .. strip_base + ctas*G - 1; the last strip's boundary column is kept
+  // for ALL rows in a linear buffer (carry_out: same entries as the ring, batch j at [j*ST_GE],
+  // no wrap, no back-pressure) that the first CTA of the next pass reads as carry_in.
+  int strip_base;
+  const uint4 *carry_in;
+  uint4 *carry_out;
   int *abort_flag;
   const double *logtab;  // 8-byte table, LOGTAB_N entries (fill_common.cuh)
   int ncons;       // consumer warps per strip in use (tuning knob)
@@ -646,9 +653,17 @@ __device__ __forceinline__ void st_volatile_v4(uint4 *p, uint4 v) {
   asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-__device__ void strip_loader(const StripParams &P, BRing *ring, int delta, int lane, int bidx, int jlast) {
-  // boundary bidx is written by the CTA to the left; batches delta .. jlast are needed here
-  const uint4 *g = P.gring + (size_t)bidx * (ST_NBG * ST_GE);
+/* a boundary in global memory: ring of ST_NBG batches with the reader's progress word, or (mask = ~0,
+ * taken = NULL) the linear carry buffer between two passes */
+struct GBound {
+  uint4 *g;
+  unsigned mask;
+  int *taken;
+};
+
+__device__ void strip_loader(const StripParams &P, BRing *ring, int delta, int lane, const GBound gb, int jlast) {
+  // the boundary is written by the CTA to the left (or by the previous pass); batches delta .. jlast are needed here
+  const uint4 *g = gb.g;
   constexpr int NP = 4;  // batches polled per pass (loads in flight per lane)
   int c_t = -1, pub = delta - 1;
   long long t0 = clock64();
@@ -662,7 +677,7 @@ __device__ void strip_loader(const StripParams &P, BRing *ring, int delta, int l
     for (int u = 0; u < NP; u++) {
       const int j = next + u;
       v[u] = make_uint4(0, 0, 0, 0);
-      if (j <= lim && lane < ST_GE) v[u] = ld_volatile_v4(&g[(size_t)(j & (ST_NBG - 1)) * ST_GE + lane]);
+      if (j <= lim && lane < ST_GE) v[u] = ld_volatile_v4(&g[(size_t)((unsigned)j & gb.mask) * ST_GE + lane]);
     }
     int got = 0;
 #pragma unroll
@@ -684,7 +699,7 @@ __device__ void strip_loader(const StripParams &P, BRing *ring, int delta, int l
       const int hi = next + got - 1;
       if (lane == 0) {
         st_vol(&ring->written, hi);
-        if (hi - pub >= ST_NBG / 4 || hi == jlast) st_vol(P.gtaken + bidx, hi);
+        if (gb.taken && (hi - pub >= ST_NBG / 4 || hi == jlast)) st_vol(gb.taken, hi);
       }
       if (hi - pub >= ST_NBG / 4) pub = hi;
       next = hi + 1;
@@ -702,22 +717,22 @@ __device__ void strip_loader(const StripParams &P, BRing *ring, int delta, int l
   }
 }
 
-__device__ void strip_flusher(const StripParams &P, BRing *ring, int last, int lane, int bidx) {
-  uint4 *g = P.gring + (size_t)bidx * (ST_NBG * ST_GE);
-  int c_w = -1, c_t = -1;
+__device__ void strip_flusher(const StripParams &P, BRing *ring, int last, int lane, const GBound gb) {
+  uint4 *g = gb.g;
+  int c_w = -1, c_t = gb.taken ? -1 : 0x3fffffff;  // the carry buffer holds every batch: nothing to wait for
   for (int next = 0; next <= last;) {
     if (!ctr_wait<false, ST_HELPER_SLEEP>(&ring->written, next, P.abort_flag, c_w)) return;
-    if (!ctr_wait<true, 64>(P.gtaken + bidx, next - ST_NBG, P.abort_flag, c_t)) return;
+    if (gb.taken && !ctr_wait<true, 64>(gb.taken, next - ST_NBG, P.abort_flag, c_t)) return;
     int hi = c_w < last ? c_w : last;
-    if (hi > c_t + ST_NBG) hi = c_t + ST_NBG;
+    if (gb.taken && hi > c_t + ST_NBG) hi = c_t + ST_NBG;
     for (int j = next; j <= hi; j++) {
       const unsigned seq = (unsigned)(j + 1);
       if (lane < ST_B) {
         const double x = ring->x[(j & (ST_NBR - 1)) * ST_B + lane];
-        st_volatile_v4(&g[(size_t)(j & (ST_NBG - 1)) * ST_GE + lane],
+        st_volatile_v4(&g[(size_t)((unsigned)j & gb.mask) * ST_GE + lane],
                        make_uint4((unsigned)__double2loint(x), seq, (unsigned)__double2hiint(x), seq));
       } else if (lane == ST_B) {
-        st_volatile_v4(&g[(size_t)(j & (ST_NBG - 1)) * ST_GE + lane],
+        st_volatile_v4(&g[(size_t)((unsigned)j & gb.mask) * ST_GE + lane],
                        make_uint4((unsigned)ring->e[j & (ST_NBR - 1)], seq, 0u, seq));
       }
     }
@@ -737,11 +752,11 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 1) fill_strip_kernel(const Stri
   SM &sm = *reinterpret_cast<SM *>(smem_raw);
   const int table = blockIdx.x / P.ctas, cta = blockIdx.x % P.ctas;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int strip0 = cta * G;
+  const int strip0 = P.strip_base + cta * G;  // strips are numbered over the whole table, passes included
   int nloc = P.P - strip0;  // strips of this CTA
   if (nloc > G) nloc = G;
   const StripTable tb = P.tables[table];
-  const bool cta_left = cta > 0, cta_right = strip0 + nloc < P.P;
+  const bool cta_left = strip0 > 0, cta_right = strip0 + nloc < P.P;
 
   for (int i = threadIdx.x; i < LOGTAB_N * LOGTAB_REP8; i += blockDim.x) sm.logtab[i] = P.logtab[i / LOGTAB_REP8];
   if (threadIdx.x < G) {
@@ -774,12 +789,34 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 1) fill_strip_kernel(const Stri
     if (cta_left) {
       const StripGeom g = strip_geom(P, strip0);
       const int jlast = strip_geom(P, strip0 - 1).nbatch - 1;
-      strip_loader(P, &sm.ring[0], g.delta, lane, table * P.ctas + cta - 1, jlast);
+      GBound gb;
+      if (cta > 0) {
+        const int bidx = table * P.ctas + cta - 1;
+        gb.g = P.gring + (size_t)bidx * (ST_NBG * ST_GE);
+        gb.mask = ST_NBG - 1;
+        gb.taken = P.gtaken + bidx;
+      } else {  // first CTA of a later pass
+        gb.g = const_cast<uint4 *>(P.carry_in);
+        gb.mask = 0xffffffffu;
+        gb.taken = NULL;
+      }
+      strip_loader(P, &sm.ring[0], g.delta, lane, gb, jlast);
     }
   } else if (warp == ST_FLUSHER) {
     if (cta_right) {
       const StripGeom g = strip_geom(P, strip0 + nloc - 1);
-      strip_flusher(P, &sm.ring[nloc], g.nbatch - 1, lane, table * P.ctas + cta);
+      GBound gb;
+      if (cta + 1 < P.ctas) {
+        const int bidx = table * P.ctas + cta;
+        gb.g = P.gring + (size_t)bidx * (ST_NBG * ST_GE);
+        gb.mask = ST_NBG - 1;
+        gb.taken = P.gtaken + bidx;
+      } else {  // last CTA of a pass that is not the last
+        gb.g = P.carry_out;
+        gb.mask = 0xffffffffu;
+        gb.taken = NULL;
+      }
+      strip_flusher(P, &sm.ring[nloc], g.nbatch - 1, lane, gb);
     }
   } else {
     // consumers: dealt round-robin to the CTA's strips.  A waiter may be at most one phase ahead
@@ -830,6 +867,8 @@ struct StripState {
   StripTable *tables;  // device array
   int tables_cap;
   long long *dbg;  // STB_PROFILE_PRODUCER builds only
+  uint4 *carry[2];  // boundary column between two passes over the columns (tables wider than one launch)
+  size_t carry_cap; // entries each
 };
 
 inline void strip_state_free(StripState *st) {
@@ -838,6 +877,8 @@ inline void strip_state_free(StripState *st) {
   cudaFree(st->logtab);
   cudaFree(st->tables);
   cudaFree(st->dbg);
+  cudaFree(st->carry[0]);
+  cudaFree(st->carry[1]);
   memset(st, 0, sizeof *st);
 }
 
@@ -905,7 +946,7 @@ struct StripPlan {
  * shapes are (K columns per lane, G strips per CTA) = (5,1), (7,1), (1,4), (3,2): up to 160, 224,
  * 128 and 192 columns per CTA, tried in that order (measured best first).
  */
-inline bool strip_plan(unsigned M, int slots, size_t elem_size, StripPlan *pl) {
+inline bool strip_plan(unsigned M, int slots, size_t elem_size, StripPlan *pl, bool multipass = false) {
   // measured best first: ONE strip per CTA with 5 (up to 160 columns) or 7 (up to 224) columns per
   // lane; the multi-strip shapes are kept for STB_STRIP_K experiments and the geometry-independence test
   static const int shapes[4][2] = {{5, 1}, {7, 1}, {1, 4}, {3, 2}};
@@ -916,7 +957,9 @@ inline bool strip_plan(unsigned M, int slots, size_t elem_size, StripPlan *pl) {
   const unsigned per_cta = (M + (unsigned)slots - 1) / (unsigned)slots;  // columns per CTA with every slot in use
   for (int i = 0; i < 4; i++) {
     const int k = shapes[i][0], gg = shapes[i][1];
-    if (force_k ? k != force_k : (unsigned)(32 * k * gg) < per_cta) continue;
+    // several passes over the columns: the widest single-strip shape, however many CTAs it takes
+    if (multipass ? (force_k ? k != force_k : !(k == 7 && gg == 1)) : (force_k ? k != force_k : (unsigned)(32 * k * gg) < per_cta))
+      continue;
     int L;
     if (gg == 1) {
       // Full warps and as FEW CTAs as the table needs beat an even spread over all SMs: the row rate
@@ -939,7 +982,7 @@ inline bool strip_plan(unsigned M, int slots, size_t elem_size, StripPlan *pl) {
     pl->C = L * k;
     pl->P = (int)((M + (unsigned)pl->C - 1) / (unsigned)pl->C);
     pl->ctas = (pl->P + gg - 1) / gg;
-    if (pl->ctas > slots) continue;
+    if (pl->ctas > slots && !multipass) continue;
     return true;
   }
   return false;
@@ -979,11 +1022,35 @@ inline int strip_fill(StripState *st, const StripFillArgs &A, cudaStream_t strea
     per_launch = strip_tables_per_launch(A.M, A.num_sms);
     if (per_launch > A.ntables) per_launch = A.ntables;
   }
-  if (!strip_plan(A.M, A.num_sms / per_launch, A.is_float ? 4 : 8, &pl)) {
-    snprintf(err, errlen, "strip_fill: M=%u needs more than one pass over the columns (not supported)", A.M);
-    return -1;
+  int slots = A.num_sms / per_launch;
+  if (const char *sv = getenv("STB_STRIP_SLOTS")) {  // testing: fewer CTAs per launch (forces several passes)
+    const int v = atoi(sv);
+    if (v > 0 && v < slots) slots = v;
   }
-  cudaError_t e = strip_state_prepare(st, per_launch * pl.ctas, A.ntables);
+  int passes = 1;
+  if (!strip_plan(A.M, slots, A.is_float ? 4 : 8, &pl)) {
+    // wider than one launch's CTAs can hold: several passes over the columns, the boundary column
+    // between two passes kept for all rows in a linear buffer (one table at a time only)
+    if (A.ntables > 1 || !strip_plan(A.M, slots, A.is_float ? 4 : 8, &pl, true)) {
+      snprintf(err, errlen, "strip_fill: M=%u does not fit %d CTAs per table", A.M, slots);
+      return -1;
+    }
+    passes = (pl.ctas + slots - 1) / slots;
+  }
+  const int ctas_total = pl.ctas, ctas_pass = passes > 1 ? slots : pl.ctas;
+  cudaError_t e = strip_state_prepare(st, per_launch * ctas_pass, A.ntables);
+  if (e == cudaSuccess && passes > 1) {
+    const size_t need = ((size_t)((A.N + 32u + 32u) >> ST_SH) + 2) * ST_GE;
+    if (need > st->carry_cap) {
+      cudaFree(st->carry[0]);
+      cudaFree(st->carry[1]);
+      st->carry[0] = st->carry[1] = NULL;
+      st->carry_cap = 0;
+      e = cudaMalloc(&st->carry[0], need * sizeof(uint4));
+      if (e == cudaSuccess) e = cudaMalloc(&st->carry[1], need * sizeof(uint4));
+      if (e == cudaSuccess) st->carry_cap = need;
+    }
+  }
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(st->tables, A.tables, (size_t)A.ntables * sizeof(StripTable), cudaMemcpyHostToDevice, stream);
   if (e != cudaSuccess) {
@@ -997,7 +1064,10 @@ inline int strip_fill(StripState *st, const StripFillArgs &A, cudaStream_t strea
   P.C = pl.C;
   P.L = pl.L;
   P.P = pl.P;
-  P.ctas = pl.ctas;
+  P.ctas = ctas_pass;
+  P.strip_base = 0;
+  P.carry_in = NULL;
+  P.carry_out = NULL;
   P.gring = st->gring;
   P.gtaken = st->gctr;
   P.abort_flag = st->gctr + st->cap;
@@ -1012,16 +1082,25 @@ inline int strip_fill(StripState *st, const StripFillArgs &A, cudaStream_t strea
   cudaMemsetAsync(st->dbg, 0, (1024 * 8 + 1024 * ST_WARPS * 4) * sizeof(long long), stream);
   P.dbg = st->dbg;
 #endif
-  for (int t0 = 0; t0 < A.ntables && e == cudaSuccess; t0 += per_launch) {
+  for (int t0 = 0, pass = 0; t0 < A.ntables && e == cudaSuccess; pass + 1 < passes ? ++pass : (pass = 0, t0 += per_launch)) {
     const int nt = (A.ntables - t0 < per_launch) ? A.ntables - t0 : per_launch;
+    const bool last_launch = t0 + per_launch >= A.ntables && pass + 1 == passes;
     P.tables = st->tables + t0;
+    if (passes > 1) {
+      P.strip_base = pass * ctas_pass * pl.G;
+      P.ctas = (ctas_total - pass * ctas_pass < ctas_pass) ? ctas_total - pass * ctas_pass : ctas_pass;
+      P.carry_in = pass > 0 ? st->carry[(pass - 1) & 1] : NULL;
+      P.carry_out = pass + 1 < passes ? st->carry[pass & 1] : NULL;
+      if (P.carry_out) e = cudaMemsetAsync(P.carry_out, 0, st->carry_cap * sizeof(uint4), stream);
+      if (e != cudaSuccess) break;
+    }
     // reader progress starts at -1 ("nothing taken"), the abort flag at 0, the ring's flags at 0
     e = cudaMemsetAsync(st->gctr, 0xFF, (size_t)st->cap * sizeof(int), stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(P.abort_flag, 0, sizeof(int), stream);
     if (e == cudaSuccess)
-      e = cudaMemsetAsync(st->gring, 0, (size_t)nt * pl.ctas * ST_NBG * ST_GE * sizeof(uint4), stream);
+      e = cudaMemsetAsync(st->gring, 0, (size_t)nt * P.ctas * ST_NBG * ST_GE * sizeof(uint4), stream);
     if (e != cudaSuccess) break;
-    const int nctas = nt * pl.ctas;
+    const int nctas = nt * P.ctas;
     const bool hs = A.has_S != 0, hv = A.has_V != 0, fl = A.is_float != 0;
     if (pl.K == 1)
       e = dispatch_strip<1, 4>(P, nctas, hs, hv, fl, stream);
@@ -1034,7 +1113,7 @@ inline int strip_fill(StripState *st, const StripFillArgs &A, cudaStream_t strea
     if (e == cudaSuccess) {
       // the abort flag is checked per launch: a later memset must not hide it
       int flag = 0;
-      if (t0 + per_launch >= A.ntables) cudaEventRecord(ev_end, stream);
+      if (last_launch) cudaEventRecord(ev_end, stream);
       e = cudaMemcpyAsync(&flag, P.abort_flag, sizeof(int), cudaMemcpyDeviceToHost, stream);
       if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
 #ifdef STB_PROFILE_PRODUCER

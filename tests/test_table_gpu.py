@@ -271,3 +271,24 @@ def test_random_shapes_match_oracle():
         else:
             _compare_full(t, N, M, a, 1e-12)
         t.free()
+
+
+@pytest.mark.parametrize("slots", [1, 2, 3])
+def test_several_passes_over_the_columns(slots, monkeypatch):
+    """Tables wider than one launch's CTAs can hold are filled in passes, the boundary column
+    carried between passes in a linear buffer.  STB_STRIP_SLOTS shrinks a launch to `slots` CTAs so
+    that a small table needs 2..5 passes: every cell against the oracle, and bit-identical to the
+    single-pass fill."""
+    N, M, a = 1500, 1000, 0.6
+    monkeypatch.delenv("STB_STRIP_SLOTS", raising=False)
+    base = stb.Table(N, M, N, M, a, FLAGS)
+    monkeypatch.setenv("STB_STRIP_SLOTS", str(slots))
+    t = stb.Table(N, M, N, M, a, FLAGS)
+    gS, gV, _, _ = _compare_full(t, N, M, a, 1e-12)
+    for which, g in ((0, gS), (1, gV)):
+        mask = harness.valid_mask(N, M, which == 1)
+        assert np.array_equal(g[mask], base.rows(which, 1, N)[:, :M][mask])
+    t.remake(0.3)  # and again through S_remake
+    _compare_full(t, N, M, 0.3, 1e-12)
+    t.free()
+    base.free()

@@ -64,3 +64,28 @@ def test_config3_shape_with_V():
     k = mm >= 3
     assert np.allclose(np.log(v[k]), (s0 - sm)[k], rtol=0, atol=2e-9)
     t.free()
+
+
+def test_table_wider_than_one_launch():
+    """M = 36 000 > 148 x 224 columns: two passes over the columns on a real B200.  Its first
+    20 000 columns are the columns of a single-pass M = 20 000 table (a table's columns do not
+    depend on M) bit for bit; across the pass boundary and in the last column the stored values
+    satisfy the recurrence S^n_m = logadd(log(n-1-m a) + S^{n-1}_m, S^{n-1}_{m-1}) to 1e-12."""
+    N, Mw, Ms, a = 37000, 36000, 20000, 0.55
+    wide = stb.Table(N, Mw, N, Mw, a, stb.S_STABLE | stb.S_NOMIRROR)
+    ref = stb.Table(N, Ms, N, Ms, a, stb.S_STABLE | stb.S_NOMIRROR)
+    for n in (2, 777, 20000, 20001, 36999, 37000):
+        rw = wide.rows(0, n, 1)[0]
+        rr = ref.rows(0, n, 1)[0]
+        top = min(n, Ms)
+        assert np.array_equal(rw[:top], rr[:top]), n
+    last = wide.rows(0, 36990, 11)
+    assert np.isfinite(last[:, :36000]).all()
+    assert wide.S(36000, 36000) == 0.0 and wide.S(37000, 36000) > 0
+    r0, r1 = wide.rows(0, 36999, 1)[0], wide.rows(0, 37000, 1)[0]
+    m = np.array([30000, 33152, 33153, 33154, 35990, 36000])  # 33152 = 148 x 224: the pass boundary
+    lhs = r1[m - 1]
+    rhs = np.logaddexp(np.log(36999 - m * a) + r0[m - 1], r0[m - 2])
+    assert np.allclose(lhs, rhs, rtol=1e-12, atol=0)
+    wide.free()
+    ref.free()
