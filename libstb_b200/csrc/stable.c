@@ -42,15 +42,23 @@ struct stb_table_impl {
   /* lazy mirrors: one pinned block of blk_rows rows per slot, fetched on first touch */
   unsigned blk_rows, nblk;
   double **blkS, **blkV;
-  pthread_mutex_t mutex;
+  /* S_THREADS (lib/stable.h:43, lib/stable.c:572-580): look-ups from several threads, growth
+   * serialised.  Growth here refills the table and drops the host mirror, so look-ups hold the
+   * lock shared while they read and growth holds it exclusively; fetching a lazy mirror block
+   * (done under the shared lock) has its own mutex. */
+  pthread_rwlock_t rw;
+  pthread_mutex_t fetch_mutex;
   int locking;
 };
 
-static void lock(stable_t *sp) {
-  if (sp->impl->locking) pthread_mutex_lock(&sp->impl->mutex);
+static void lock(stable_t *sp) { /* exclusive: growth, refill */
+  if (sp->impl->locking) pthread_rwlock_wrlock(&sp->impl->rw);
 }
 static void unlock(stable_t *sp) {
-  if (sp->impl->locking) pthread_mutex_unlock(&sp->impl->mutex);
+  if (sp->impl->locking) pthread_rwlock_unlock(&sp->impl->rw);
+}
+static void rlock(stable_t *sp) { /* shared: reading cells */
+  if (sp->impl->locking) pthread_rwlock_rdlock(&sp->impl->rw);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -112,7 +120,7 @@ static double *mirror_fetch(stable_t *sp, int which, unsigned b) {
   struct stb_table_impl *im = sp->impl;
   double **tab = which == STB_TAB_S ? im->blkS : im->blkV;
   double *blk;
-  lock(sp);
+  if (im->locking) pthread_mutex_lock(&im->fetch_mutex);
   blk = tab[b];
   if (!blk) {
     unsigned row0 = b * im->blk_rows, rows = im->blk_rows;
@@ -125,23 +133,30 @@ static double *mirror_fetch(stable_t *sp, int which, unsigned b) {
     /* publish only after the block is complete: readers are lock-free */
     __atomic_store_n(&tab[b], blk, __ATOMIC_RELEASE);
   }
-  unlock(sp);
+  if (im->locking) pthread_mutex_unlock(&im->fetch_mutex);
   return blk;
 }
 
 /* cell (n,m), 1<=m<=n<=usedN, m<=usedM */
 static double cell(stable_t *sp, int which, unsigned n, unsigned m) {
   struct stb_table_impl *im = sp->impl;
-  const double *full = which == STB_TAB_S ? im->fullS : im->fullV;
-  if (full) return full[(size_t)(n - 1) * im->ld + (m - 1)];
+  double v;
+  rlock(sp);
   {
-    double **tab = which == STB_TAB_S ? im->blkS : im->blkV;
-    unsigned b = (n - 1) / im->blk_rows;
-    double *blk = __atomic_load_n(&tab[b], __ATOMIC_ACQUIRE);
-    if (!blk && !(blk = mirror_fetch(sp, which, b)))
-      yaps_quit("stable: device read failed: %s\n", stb_cuda_last_error());
-    return blk[(size_t)((n - 1) % im->blk_rows) * im->ld + (m - 1)];
+    const double *full = which == STB_TAB_S ? im->fullS : im->fullV;
+    if (full)
+      v = full[(size_t)(n - 1) * im->ld + (m - 1)];
+    else {
+      double **tab = which == STB_TAB_S ? im->blkS : im->blkV;
+      unsigned b = (n - 1) / im->blk_rows;
+      double *blk = __atomic_load_n(&tab[b], __ATOMIC_ACQUIRE);
+      if (!blk && !(blk = mirror_fetch(sp, which, b)))
+        yaps_quit("stable: device read failed: %s\n", stb_cuda_last_error());
+      v = blk[(size_t)((n - 1) % im->blk_rows) * im->ld + (m - 1)];
+    }
   }
+  unlock(sp);
+  return v;
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -200,7 +215,8 @@ stable_t *S_make(unsigned initN, unsigned initM, unsigned maxN, unsigned maxM, d
   sp->usedN = initN;
   sp->usedM = initM;
   sp->usedN1 = initN;
-  pthread_mutex_init(&im->mutex, NULL);
+  pthread_rwlock_init(&im->rw, NULL);
+  pthread_mutex_init(&im->fetch_mutex, NULL);
   im->locking = (flags & S_THREADS) != 0;
   im->algo = (flags & S_MIRROR_ORDER) ? STB_FILL_MIRROR : STB_FILL_LINEAR;
   {
@@ -314,7 +330,13 @@ double S_S1(stable_t *sp, unsigned n) {
     unlock(sp);
     return v;
   }
-  return sp->S1[n - 1];
+  {
+    double v;
+    rlock(sp); /* growth may move the vector */
+    v = sp->S1[n - 1];
+    unlock(sp);
+    return v;
+  }
 }
 
 /* lib/stable.c:875-883 */
@@ -392,7 +414,8 @@ void S_free(stable_t *sp) {
   if (sp->impl) {
     mirror_drop(sp);
     stb_cuda_table_destroy(sp->impl->dev);
-    pthread_mutex_destroy(&sp->impl->mutex);
+    pthread_rwlock_destroy(&sp->impl->rw);
+    pthread_mutex_destroy(&sp->impl->fetch_mutex);
     free(sp->impl);
   }
   free(sp->tag);

@@ -292,3 +292,36 @@ def test_several_passes_over_the_columns(slots, monkeypatch):
     _compare_full(t, N, M, 0.3, 1e-12)
     t.free()
     base.free()
+
+
+def test_concurrent_lookups_with_growth_S_THREADS():
+    """S_THREADS (lib/stable.h:43): look-ups from several threads while the table grows on demand
+    (growth refills the table and replaces the host mirror, so readers hold a shared lock).
+    ctypes releases the GIL during the C calls, so the eight threads really overlap."""
+    import threading
+
+    N0, M0, Nmax, Mmax, a = 200, 40, 6000, 300, 0.45
+    t = stb.Table(N0, M0, Nmax, Mmax, a, FLAGS | stb.S_THREADS)
+    S, V = harness.oracle_tables(Nmax, Mmax, a)
+    errs = []
+
+    def work(seed):
+        rng = np.random.default_rng(seed)
+        top = 300
+        for it in range(400):
+            top = min(Nmax - 2, int(top * 1.02) + 5)  # reach further and further: growth on the way
+            n = int(rng.integers(3, top))
+            m = int(rng.integers(2, min(n, Mmax - 2)))
+            s, v = t.S(n, m), t.V(n, m)
+            if not (abs(s - S[n - 1, m - 1]) <= 1e-12 * max(1.0, abs(S[n - 1, m - 1])) and
+                    abs(v - V[n - 1, m - 1]) <= 1e-12 * max(1.0, abs(V[n - 1, m - 1]))):
+                errs.append((n, m, s, S[n - 1, m - 1], v, V[n - 1, m - 1]))
+
+    threads = [threading.Thread(target=work, args=(100 + i,)) for i in range(8)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errs, errs[:3]
+    assert t.usedN > N0 and t.usedM > M0
+    t.free()
