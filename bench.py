@@ -467,7 +467,12 @@ def run_own(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "stb::fill_strip_kernel",
                          "kernel_ms": kern_ms,
-                         "fp64_pipe": {"note": "second bound, see DESIGN.md", "cells_per_s": cells / (kern_ms * 1e-3)}},
+                         # the second bound (SURVEY.md 8d asks for both): 2 recurrence + 7 logarithm FP64
+                         # instructions per stored S cell against the DFMA rate measured on a B200 with
+                         # tools/ubench.cu (1.856e13 warp-lane instr/s = 37.1 TFLOP/s)
+                         "fp64_pipe": {"instr_per_cell": 9, "peak_instr_per_s": 1.856e13,
+                                       "peak_source": "tools/ubench.cu on B200 (DESIGN.md 3.1)",
+                                       "frac": cells / (kern_ms * 1e-3) * 9 / 1.856e13}},
             "clocks": clocks,
         }
         if cpu:
