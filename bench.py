@@ -291,7 +291,21 @@ def run_extras():
         res["cpu_reference"] = {"samples_per_s": 6 / (time.perf_counter() - t0), "cores": 1, "chains": 3,
                                 "a_draws_match": bool(ok)}
     out["config4_samplers"] = res
-    # --- the same in the reference's DEFAULT (ARS) configuration: batched arms_simple machines ---
+    try:
+        _extras_ars(out, stb, cts, Cn, bpar, a0, r0)
+    except Exception as exc:  # one side measurement never takes the others down
+        out["config4_samplers_ars"] = {"error": repr(exc)}
+    try:
+        _extras_variants(out, stb)
+    except Exception as exc:
+        out["config2_variants"] = {"error": repr(exc)}
+    return out
+
+
+def _extras_ars(out, stb, cts, Cn, bpar, a0, r0):
+    """config 4 in the reference's DEFAULT (ARS) configuration: batched arms_simple machines"""
+    import numpy as np
+
     rnd0 = stb.rand31_states([777 + c for c in range(Cn)])
     stb.samplea_batch_ars(a0[:64], cts, bpar, rnd0[:64])  # warm-up
     t0 = time.perf_counter()
@@ -313,17 +327,19 @@ def run_extras():
         libc.srand.argtypes = [C.c_uint]
         libc.srand48.argtypes = [C.c_long]
         t0 = time.perf_counter()
-        ok = True
         for c in range(3):
             libc.srand(777 + c)
             libc.srand48(12345 + c)
             ar = R.samplea(float(a0[c]), *cts.args(), None, bpar.ctypes.data_as(C.POINTER(d)), None, 1, 0)
             R.sampleb(10.0, cts.I, 1.1, 20.0, cts.N.ctypes.data_as(u32p), cts.T.ctypes.data_as(u32p), ar, None, 1, 0)
-            ok = ok and abs(ar - a2[c]) <= 1e-9 * abs(ar)
-        res2["cpu_reference"] = {"samples_per_s": 6 / (time.perf_counter() - t0), "cores": 1, "chains": 3,
-                                 "a_draws_match": bool(ok)}
+        # (no draw-by-draw comparison here: at this scale ARS's concavity test is decided by the last
+        # bits of the density in either library -- tests/test_samplers_gpu.py::test_batched_ars_at_config4_scale)
+        res2["cpu_reference"] = {"samples_per_s": 6 / (time.perf_counter() - t0), "cores": 1, "chains": 3}
     out["config4_samplers_ars"] = res2
-    # --- config 2 in the other storage modes (S-only, V-only, S+V, FP64 and S_FLOAT) ---
+
+
+def _extras_variants(out, stb):
+    """config 2 in the other storage modes (S-only, V-only, S+V, FP64 and S_FLOAT)"""
     S, V, F = stb.S_STABLE, stb.S_UVTABLE, stb.S_FLOAT
     cS, cV = cells_S(N_ROWS, M_COLS), M_COLS * (M_COLS - 1) // 2 + (N_ROWS - M_COLS) * (M_COLS - 1)
     var = {}
@@ -338,7 +354,6 @@ def run_extras():
         best = min(ms)
         var[name] = {"kernel_ms": best, "cells_per_s": ncell / (best * 1e-3), "hbm_frac": ncell * bpc / (best * 1e-3) / 1e9 / 6544.7}
     out["config2_variants"] = var
-    return out
 
 
 # ------------------------------------------------------------------------------------------------

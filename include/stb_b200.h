@@ -79,6 +79,15 @@ typedef struct stb_rand31 {
 void stb_rand31_seed(stb_rand31_t *g, unsigned seed);
 int stb_rand31_next(stb_rand31_t *g);
 
+/*
+ * arms_simple(3, &lo[c], &hi[c], myfunc, mydata, 0, ., &x[c]) (include/arms.h) for C independent
+ * chains advanced in lock-step, chain c drawing its uniforms from rnd[c]: the driver of the batched
+ * ARS samplers with a host log-density.  A chain whose sampler stops with an arms() error code keeps
+ * x[c]; *nfailed (may be NULL) counts them.  Returns 0, or a negative value when memory runs out.
+ */
+int stb_arms_simple_batch(double *x, size_t C, const double *lo, const double *hi, stb_rand31_t *rnd,
+                          double (*myfunc)(double x, void *mydata), void *mydata, size_t *nfailed);
+
 /* frees device memory the batched samplers keep between calls (the sweep handle of the last
  * stb_samplea_batch: one launch's worth of table slabs) */
 void stb_release_caches(void);

@@ -97,6 +97,8 @@ def lib() -> C.CDLL:
     L.stb_rng48_beta.restype, L.stb_rng48_beta.argtypes = d, [u64p, d, d]
     L.stb_rand31_seed.restype, L.stb_rand31_seed.argtypes = None, [vp, C.c_uint]
     L.stb_rand31_next.restype, L.stb_rand31_next.argtypes = C.c_int, [vp]
+    L.stb_arms_simple_batch.restype = C.c_int
+    L.stb_arms_simple_batch.argtypes = [dp, C.c_size_t, dp, dp, vp, POST, vp, C.POINTER(C.c_size_t)]
     L.stb_samplea_batch_ars.restype = C.c_int
     L.stb_samplea_batch_ars.argtypes = [dp, C.c_size_t, C.c_int, ip, u32p, C.POINTER(u32p),
                                         C.POINTER(C.POINTER(C.c_uint16)), dp, C.c_int, vp, vp]

@@ -190,11 +190,15 @@ int stb_rand31_next(stb_rand31_t *g) { return stb_rand31_step(g); }
  * One arms_simple(3, lo, hi, ...) per chain (envelope of at most 100 knots, no Metropolis step:
  * lib/arms.c:98-123 as samplea / sampleb call it), every chain a resumable machine on its own
  * rand() stream.  Each round evaluates the one point every unfinished chain is waiting for.
- * xp[c] receives the draw.  Returns 0, -1/-2 (memory / evaluation failure), or 1 + the index of
- * the first chain whose sampler reported an error (its arms() code goes to stderr).
+ * xp[c] receives the draw.  A chain whose sampler stops with an arms() error code -- 2000: the
+ * log-posterior is not concave on its interval, 2001: a hundred proposals -- keeps the value it
+ * came with: that is what the reference does (samplea / sampleb ignore arms_simple's return value,
+ * lib/samplea.c:210-211, lib/sampleb.c:135, and the sample variable still holds its input); the
+ * number of such chains is returned through *nfailed.  Returns 0, or -1/-2 (memory / evaluation
+ * failure).
  */
 static int ars_lockstep(double *xp, size_t C, const double *lo, const double *hi, stb_rand31_t *rnd, eval_fn eval,
-                        void *ctx, stb_sample_stats *st) {
+                        void *ctx, stb_sample_stats *st, size_t *nfailed) {
   stb_ars_t **m = (stb_ars_t **)calloc(C, sizeof *m);
   int *state = (int *)malloc(sizeof(int) * C), *chain = (int *)malloc(sizeof(int) * C);
   double *want = (double *)malloc(sizeof(double) * C), *xq = (double *)malloc(sizeof(double) * C);
@@ -222,10 +226,6 @@ static int ars_lockstep(double *xp, size_t C, const double *lo, const double *hi
       if (state[c] == STB_ARS_NEED) {
         xq[cnt] = want[c];
         chain[cnt++] = (int)c;
-      } else if (state[c] != STB_ARS_DONE) {
-        fprintf(stderr, "arms_simple: error %d (chain %zu, bounds [%lg,%lg])\n", state[c], c, lo[c], hi[c]);
-        rc = 1 + (int)c;
-        goto done;
       }
     }
     if (!cnt) break;
@@ -243,6 +243,11 @@ static int ars_lockstep(double *xp, size_t C, const double *lo, const double *hi
       state[c] = stb_ars_feed(m[c], val[j], &want[c]);
     }
   }
+  if (nfailed) {
+    *nfailed = 0;
+    for (c = 0; c < C; c++)
+      if (state[c] != STB_ARS_DONE) ++*nfailed;
+  }
 done:
   if (m)
     for (c = 0; c < C; c++) stb_ars_free(m[c]);
@@ -253,6 +258,30 @@ done:
   free(xq);
   free(val);
   return rc;
+}
+
+/* arms_simple(3, ...) for C independent chains with a HOST log-density: the lock-step driver with
+ * the evaluations done one by one (include/stb_b200.h).  Chains whose sampler fails keep x[c]. */
+typedef struct {
+  double (*f)(double, void *);
+  void *data;
+} HostDensity;
+
+static int host_density_eval(void *ctx, const double *x, const int *chain, size_t cnt, double *out) {
+  HostDensity *h = (HostDensity *)ctx;
+  size_t j;
+  (void)chain;
+  for (j = 0; j < cnt; j++) out[j] = h->f(x[j], h->data);
+  return 0;
+}
+
+int stb_arms_simple_batch(double *x, size_t C, const double *lo, const double *hi, stb_rand31_t *rnd,
+                          double (*myfunc)(double x, void *mydata), void *mydata, size_t *nfailed) {
+  HostDensity h;
+  h.f = myfunc;
+  h.data = mydata;
+  if (!C) return 0;
+  return ars_lockstep(x, C, lo, hi, rnd, host_density_eval, &h, NULL, nfailed);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -367,7 +396,7 @@ static int samplea_batch_core(double *a, size_t C, int I, const int *K, const sc
   ab.bpar_per_chain = bpar_per_chain;
   ab.st = st;
   if (rnd) {
-    rc = ars_lockstep(a, C, lo, hi, rnd, aterms_batch, &ab, st);
+    rc = ars_lockstep(a, C, lo, hi, rnd, aterms_batch, &ab, st, NULL);
     for (c = 0; rc == 0 && c < C; c++)
       if (a[c] < lo[c] || a[c] > hi[c]) {
         fprintf(stderr, "Arms_simple(apar) returned value out of bounds (chain %zu)\n", c);
@@ -562,7 +591,7 @@ static int sampleb_batch_core(double *b, size_t C, int I, double shape, double s
         rc = -1;
       else {
         for (size_t j = 0; j < cnt; j++) g2[j] = rnd[idx[j]];
-        rc = ars_lockstep(xs, cnt, lo, hi, g2, bterms_batch, &bb, sp);
+        rc = ars_lockstep(xs, cnt, lo, hi, g2, bterms_batch, &bb, sp, NULL);
         for (size_t j = 0; j < cnt; j++) rnd[idx[j]] = g2[j];
         for (size_t j = 0; rc == 0 && j < cnt; j++)
           if (xs[j] < B_MIN || xs[j] > B_MAX) {

@@ -170,3 +170,43 @@ def test_rand31_is_glibc_rand():
         libc.srand(seed)
         for _ in range(2000):
             assert L.stb_rand31_next(g.ctypes.data) == libc.rand()
+
+
+@needs_ref
+def test_lockstep_ars_is_the_scalar_sampler_chain_by_chain():
+    """stb_arms_simple_batch: the lock-step driver of the batched ARS samplers, here with a host
+    density.  Chain c on the stream of srand(seed_c) must make exactly the draw the reference's
+    arms_simple makes after srand(seed_c) -- including chains whose log-density is not concave on
+    their interval: the sampler stops with code 2000 and the value stays what it was (the
+    reference's samplea / sampleb ignore the return value, lib/samplea.c:210-215)."""
+    L, R = stb.lib(), _ref()
+    bimodal = lambda x: math.log(0.6 * math.exp(-0.5 * (x + 1.5) ** 2 / 0.3) + 0.4 * math.exp(-0.5 * (x - 1.0) ** 2 / 0.2))
+    for name, f in (("gamma", DENSITIES["gamma"][0]), ("bimodal", bimodal)):
+        Cn = 64
+        rng = np.random.default_rng(5)
+        if name == "gamma":
+            lo = rng.uniform(0.01, 1.0, Cn)
+            hi = lo + rng.uniform(2.0, 15.0, Cn)
+        else:
+            lo = rng.uniform(-4.0, -2.0, Cn)
+            hi = rng.uniform(-1.0, 4.0, Cn)  # some intervals see one mode (concave), some both
+        seeds = [3000 + c for c in range(Cn)]
+        x = np.full(Cn, -77.0)
+        cb = POST(lambda v, _: f(v))
+        nfailed = C.c_size_t(0)
+        rnd = stb.rand31_states(seeds)
+        rc = L.stb_arms_simple_batch(x.ctypes.data_as(dp), Cn, lo.ctypes.data_as(dp), hi.ctypes.data_as(dp),
+                                     rnd.ctypes.data, cb, None, C.byref(nfailed))
+        assert rc == 0
+        fails = 0
+        for c in range(Cn):
+            a, b, prev, out = C.c_double(lo[c]), C.c_double(hi[c]), C.c_double(0.0), C.c_double(-77.0)
+            libc.srand(seeds[c])
+            code = R.arms_simple(3, C.byref(a), C.byref(b), cb, None, 0, C.byref(prev), C.byref(out))
+            assert x[c] == out.value, (name, c, code)
+            libc.rand.restype = C.c_int
+            assert L.stb_rand31_next(rnd.ctypes.data + c * stb.RAND31_DTYPE.itemsize) == libc.rand(), (name, c)
+            fails += code != 0
+        assert nfailed.value == fails
+        if name == "bimodal":
+            assert fails > 0

@@ -16,6 +16,8 @@ __global__ void k(double *out, long long *cyc, double a, double b, int iters) {
       if (MODE == 0) x[i] = fma(x[i], b, a);
       if (MODE == 1) x[i] = x[i] + b;
       if (MODE == 2) x[i] = (i & 1) ? fma(x[i], b, a) : x[i] + b;
+      if (MODE == 3) x[i] = (double)(__double2loint(x[i]) + it + i);  // I2F.F64.S32 (integer -> double conversion)
+      if (MODE == 4) x[i] = __hiloint2double(0x43300000, __double2loint(x[i]) + it + i) - 4503601774854144.0;  // magic-number conversion: IADD + MOV + DADD
     }
   }
   long long t1 = clock64();
@@ -47,5 +49,7 @@ int main() {
   for (int w : {1, 4, 8, 16, 32}) run<0>("DFMA", w);
   for (int w : {1, 4, 8, 16}) run<1>("DADD", w);
   for (int w : {1, 4, 16}) run<2>("DFMA+DADD", w);
+  for (int w : {1, 4, 16}) run<3>("I2F.F64", w);
+  for (int w : {1, 4, 16}) run<4>("magic i2d", w);
   return 0;
 }
