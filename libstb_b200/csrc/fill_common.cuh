@@ -15,18 +15,15 @@
 namespace stb {
 
 constexpr int LOGTAB_N = 257;  // c_i = 1 + i/256, i = 0..256
-// In shared memory the table is kept LOGTAB_REP times, interleaved (entry i of copy j at
-// [i*8 + j]): copy j occupies only the four banks 4j..4j+3, and lane l reads copy l % 8, so the
-// eight lanes a 16-byte shared-memory load serves per pass never collide whatever their
-// mantissas are.  (One copy costs ~2.7 passes per load at random indices: measured as the largest
-// consumer of shared-memory bandwidth of the fill.)
-constexpr int LOGTAB_REP = 8;
-// The strip kernel's table holds ONLY log(c_i) (8 bytes): 1/c_i is taken from the hardware's
+// The logarithm's table holds ONLY log(c_i) (8 bytes): 1/c_i is taken from the hardware's
 // single-precision reciprocal of c_i (exactly representable, so the result is a fixed function of
 // i), widened to double with integer operations; the table is built on the device with the same
 // instruction, T[i] = -log(rcp(c_i)), which makes log(mant) = T[i] + log1p(mant*rcp(c_i) - 1) an
-// identity whatever the last bit of the reciprocal is.  Half the shared-memory traffic of the
-// 16-byte entries.  Kept LOGTAB_REP8 times (copy j in 8-byte bank j, lane l reads copy l % 16).
+// identity whatever the last bit of the reciprocal is.  In shared memory the table is kept
+// LOGTAB_REP8 times, interleaved (entry i of copy j at [i*16 + j]): copy j occupies only 8-byte
+// bank j and lane l reads copy l % 16, so the sixteen lanes a shared-memory load serves per pass
+// never collide whatever their mantissas are.  (A single copy of a 16-byte-entry table cost ~2.7
+// passes per load at random indices and was the largest user of shared-memory bandwidth of the fill.)
 constexpr int LOGTAB_REP8 = 16;
 
 __device__ __forceinline__ double logtab_inv_c(int idx) {  // rcp(1 + idx/256) as a double, idx = 0..256
@@ -36,11 +33,6 @@ __device__ __forceinline__ double logtab_inv_c(int idx) {  // rcp(1 + idx/256) a
   return __hiloint2double((int)((fb >> 3) + 0x38000000u), (int)(fb << 29));
 }
 constexpr long long FILL_WATCHDOG = 6000000000LL;  // cycles a wait may last before the fill aborts
-
-struct __align__(16) LogTabEntry {
-  double inv_c;  // 1/c_i rounded
-  double log_c;  // -log(inv_c) in double
-};
 
 __device__ __forceinline__ int ld_vol(const int *p) { return *(const volatile int *)p; }
 __device__ __forceinline__ void st_vol(int *p, int v) { *(volatile int *)p = v; }
@@ -65,30 +57,7 @@ __device__ __forceinline__ double shfl_up_d(double v) {
   return __hiloint2double(hi, lo);
 }
 
-/*
- * log(x * 2^E) for x > 0 finite normal; Eoff = (double)E - (2^52 + 2^31).
- * Table-driven: x = 2^k * mant, mant in [1,2); c = 1 + i/256 nearest to mant; r = mant/c - 1
- * (|r| <= 2^-9, one FMA); log(mant) = log1p(r) + log(c); result = (E+k) ln2 + log(c) + log1p(r)
- * with E+k formed exactly.  mant == 1 gives exactly (E+k) ln2, so S^n_n comes out as +0.0.
- */
 constexpr double LOG_EBIAS = 4503601774854144.0;  // 2^52 + 2^31
-
-__device__ __forceinline__ double log_scaled(double x, double Eoff, const LogTabEntry *tab) {
-  const int hi = __double2hiint(x), lo = __double2loint(x);
-  const int k = (hi >> 20) - 1023;
-  const int frac = hi & 0xFFFFF;
-  const int idx = (frac + 0x800) >> 12;
-  const double mant = __hiloint2double(frac | 0x3FF00000, lo);
-  const double2 tb = *reinterpret_cast<const double2 *>(tab + idx);
-  const double r = fma(mant, tb.x, -1.0);
-  double t = fma(r, 0.2, -0.25);
-  t = fma(r, t, 1.0 / 3.0);
-  t = fma(r, t, -0.5);
-  const double p = fma(r * r, t, r);
-  // (2^52 + 2^31 + k) + (E - 2^52 - 2^31) == E + k exactly
-  const double Ek = __hiloint2double(0x43300000, (int)(0x80000000u ^ (unsigned)k)) + Eoff;
-  return fma(Ek, 0.693147180559945309417232, tb.y + p);
-}
 
 /* x / d for normal positive operands: MUFU seed + two Newton steps + one correction, no branch */
 __device__ __forceinline__ double div_pos(double x, double d) {
@@ -103,29 +72,14 @@ __device__ __forceinline__ double div_pos(double x, double d) {
 }
 
 /*
- * Same value with the exponent as an integer: kbias = E + 0x80000000 - 1023 (mod 2^32), so that
- * (hi >> 20) + kbias is the low word of the double 2^52 + 2^31 + (E + k) and one subtraction of
- * the constant gives E + k exactly (|E + k| < 2^31).
+ * log(x * 2^E) for x > 0 finite normal, E given as kbias = E + 0x80000000 - 1023 (mod 2^32): then
+ * (hi >> 20) + kbias is the low word of the double 2^52 + 2^31 + (E + k), k the exponent of x, and
+ * one subtraction of that constant gives E + k exactly (|E + k| < 2^31).
+ * Table-driven: x = 2^k * mant, mant in [1,2); c = 1 + i/256 nearest to mant; r = mant*rcp(c) - 1
+ * (|r| <= 2^-9 + 2^-23, one FMA); log(mant) = log1p(r) + T[i]; result = (E+k) ln2 + T[i] + log1p(r).
+ * mant == 1 gives exactly (E+k) ln2, so S^n_n comes out as +0.0.  (tab points at this lane's copy,
+ * entries REP apart.)
  */
-template <int REP = 1>
-__device__ __forceinline__ double log_scaled_i(double x, unsigned kbias, const LogTabEntry *tab) {
-  const int hi = __double2hiint(x), lo = __double2loint(x);
-  const int frac = hi & 0xFFFFF;
-  const int idx = (frac + 0x800) >> 12;
-  const double mant = __hiloint2double(frac | 0x3FF00000, lo);
-  // REP > 1: the table is stored REP times, entry i of copy j at [i*REP + j], and tab already
-  // points at this lane's copy (see LOGTAB_REP)
-  const double2 tb = *reinterpret_cast<const double2 *>(tab + idx * REP);
-  const double r = fma(mant, tb.x, -1.0);
-  double t = fma(r, 0.2, -0.25);
-  t = fma(r, t, 1.0 / 3.0);
-  t = fma(r, t, -0.5);
-  const double p = fma(r * r, t, r);
-  const double Ek = __hiloint2double(0x43300000, (int)(((unsigned)hi >> 20) + kbias)) - LOG_EBIAS;
-  return fma(Ek, 0.693147180559945309417232, tb.y + p);
-}
-
-/* the same with the 8-byte table (tab points at this lane's copy, entries REP apart) */
 template <int REP>
 __device__ __forceinline__ double log_scaled_r(double x, unsigned kbias, const double *tab) {
   const int hi = __double2hiint(x), lo = __double2loint(x);
@@ -155,18 +109,6 @@ __global__ void logtab8_build_kernel(double *tab) {
 template <typename OutT>
 __device__ __forceinline__ void st_out(OutT *p, double v) {
   *p = (OutT)v;
-}
-
-/* host: the log table (computed in long double, rounded once) */
-inline void logtab_host(LogTabEntry *h) {
-  for (int i = 0; i < LOGTAB_N; i++) {
-    double c = 1.0 + (double)i / 256.0;
-    double inv = 1.0 / c;
-    h[i].inv_c = inv;
-    h[i].log_c = (double)(-logl((long double)inv));
-  }
-  h[0].inv_c = 1.0;
-  h[0].log_c = 0.0;
 }
 
 }  // namespace stb

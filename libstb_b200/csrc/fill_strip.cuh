@@ -141,12 +141,12 @@ struct alignas(16) StripSub {  // per strip
   // steps never wrap.
   double xring[(Cfg::RS + ST_RB) * Cfg::CP];
   double yring[HAS_V ? (Cfg::RS + ST_RB) * 32 : 2];
-  unsigned ering[ST_NJ * 32];  // E + 0x80000000 - 1023 (mod 2^32) per (producer batch, lane): log_scaled_i
+  unsigned ering[ST_NJ * 32];  // E + 0x80000000 - 1023 (mod 2^32) per (producer batch, lane): log_scaled_r
   int pad0[2];
   int progress;  // last producer batch whose sixteen steps are all in the ring (-1: none yet)
   int padp[3];
   int empty_gen[Cfg::NB];  // units (8 rows x 32 columns) of slot s finished so far: U per tenant batch
-  int next_q;
+  int pad_q;
   int pad[3];
 };
 
@@ -763,7 +763,6 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 1) fill_strip_kernel(const Stri
     auto &sb = sm.sub[threadIdx.x];
     for (int s = 0; s < Cfg::NB; s++) sb.empty_gen[s] = 0;
     sb.progress = -1;
-    sb.next_q = 0;
   }
   // boundary rings start as zeros: a strip without a left neighbour reads its (unused) ring
   for (int i = threadIdx.x; i < (G + 1) * ST_NBR * ST_B; i += blockDim.x) sm.ring[i / (ST_NBR * ST_B)].x[i % (ST_NBR * ST_B)] = 0.0;
