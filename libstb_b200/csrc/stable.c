@@ -49,6 +49,10 @@ struct stb_table_impl {
   pthread_rwlock_t rw;
   pthread_mutex_t fetch_mutex;
   int locking;
+  /* The strip kernel produces log S^n_1 on the device; the host vector S1 (S_S1, S_S(n,1)) is
+   * refreshed from it on first use after a fill, not by every fill: callers that only do batched
+   * look-ups (samplea) never pay for the copy. */
+  int s1_stale;
 };
 
 static void lock(stable_t *sp) { /* exclusive: growth, refill */
@@ -178,9 +182,8 @@ static int fill(stable_t *sp, double a, unsigned startN, unsigned startM, unsign
     sp->S1[0] = 0;
     for (n = 2; n <= N; n++) sp->S1[n - 1] = sp->S1[n - 2] + log(n - 1 - a);
   }
-  if (stb_cuda_fill(im->dev, a, startN, startM, N, M, im->algo,
-                    (mirror_order || hasS) ? sp->S1 : NULL))
-    return 1;
+  if (stb_cuda_fill(im->dev, a, startN, startM, N, M, im->algo, mirror_order ? sp->S1 : NULL)) return 1;
+  im->s1_stale = hasS && !mirror_order;
   /* a changed: forget the lazily computed tail of S1, lib/stable.c:350-353 */
   for (n = N + 1; n <= sp->usedN1; n++) sp->S1[n - 1] = 0;
   sp->usedN = N;
@@ -293,10 +296,23 @@ done:
   return result;
 }
 
+/* bring S1[0 .. usedN-1] up to date with the last fill (see s1_stale) */
+static void s1_sync(stable_t *sp) {
+  struct stb_table_impl *im = sp->impl;
+  if (!__atomic_load_n(&im->s1_stale, __ATOMIC_ACQUIRE)) return;
+  lock(sp);
+  if (im->s1_stale) {
+    if (stb_cuda_read_s1(im->dev, sp->usedN, sp->S1)) yaps_quit("stable: device read failed: %s\n", stb_cuda_last_error());
+    __atomic_store_n(&im->s1_stale, 0, __ATOMIC_RELEASE);
+  }
+  unlock(sp);
+}
+
 /* lib/stable.c:822-873 */
 double S_S1(stable_t *sp, unsigned n) {
   if (n == 0) return -HUGE_VAL;
   if (!sp->S1) return -HUGE_VAL;
+  s1_sync(sp);
   if (n > sp->usedN) {
     double v;
     if (n > sp->maxN) {

@@ -230,6 +230,18 @@ extern "C" int stb_cuda_fill(stb_dev_t *d, double a, unsigned startN, unsigned s
   return 0;
 }
 
+/* log S^n_1, n = 1..N, of the most recent fill (the strip kernel leaves the column in d->s1) */
+extern "C" int stb_cuda_read_s1(stb_dev_t *d, unsigned N, double *dst) {
+  CK(cudaSetDevice(d->device));
+  if (!d->s1 || N > d->capN) {
+    snprintf(g_err, sizeof g_err, "stb_cuda_read_s1: bad range");
+    return -1;
+  }
+  CK(cudaMemcpyAsync(dst, d->s1, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+  CK(cudaStreamSynchronize(d->stream));
+  return 0;
+}
+
 extern "C" int stb_cuda_read_rows(stb_dev_t *d, int which, unsigned row0, unsigned nrows, double *dst) {
   CK(cudaSetDevice(d->device));
   const void *tab = which == STB_TAB_S ? d->S : d->V;

@@ -59,6 +59,8 @@ size_t stb_cuda_table_bytes(const stb_dev_t *d); /* device bytes currently held 
  */
 int stb_cuda_fill(stb_dev_t *d, double a, unsigned startN, unsigned startM, unsigned N, unsigned M,
                   int algo, double *s1_host);
+/* the m = 1 column (log S^n_1, n = 1..N) the most recent strip-kernel fill left on the device */
+int stb_cuda_read_s1(stb_dev_t *d, unsigned N, double *dst);
 /* milliseconds the device spent in the most recent stb_cuda_fill (CUDA events) */
 float stb_cuda_last_fill_ms(const stb_dev_t *d);
 
