@@ -372,8 +372,15 @@ def run_own(args):
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU library)")
     torch.cuda.set_device(local)
     dist = None
+    saved_stdout = None
     if world > 1:
         import torch.distributed as dist
+
+        # stdout carries ONE JSON line: whatever libraries print there meanwhile (NCCL's version
+        # banner) goes to stderr
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line
@@ -501,6 +508,10 @@ def run_own(args):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     if rank == 0:
         print(json.dumps(line))
         if not ok:
