@@ -89,3 +89,34 @@ def test_table_wider_than_one_launch():
     assert np.allclose(lhs, rhs, rtol=1e-12, atol=0)
     wide.free()
     ref.free()
+
+
+def test_config2_recurrence_holds_across_every_cta_boundary():
+    """Full-size config 2, S and V: two million stored cells -- half of them on the two columns either
+    side of EVERY strip boundary of the launch (multiples of 160 columns), the rest uniform -- must
+    satisfy the defining recurrences from the stored row above, to 1e-12:
+        S^n_m = logadd(log(n-1-m a) + S^{n-1}_m, S^{n-1}_{m-1})              (lib/stable.c:380-388)
+        V^n_m = (1 + (n-1-m a) V^{n-1}_m) / (1/V^{n-1}_{m-1} + (n-1-(m-1)a))  (lib/stable.c:475-482)
+    A hand-off error between CTAs (boundary ring, exponents, batch phase) would break them."""
+    N, M, a = 200000, 20000, 0.7
+    t = stb.Table(N, M, N, M, a, stb.S_STABLE | stb.S_UVTABLE | stb.S_NOMIRROR)
+    rng = np.random.default_rng(5)
+    cnt = 500_000
+    edges = np.arange(160, M, 160)
+    m_edge = rng.choice(np.concatenate([edges, edges + 1]), size=cnt)
+    m_any = rng.integers(3, M + 1, size=cnt)
+    for m in (m_edge, m_any):
+        m = m.astype(np.int64)
+        n = np.maximum(m + 2, rng.integers(4, N + 1, size=cnt)).astype(np.int64)  # n-1 > m: all three cells off the diagonal's right
+        n = np.minimum(n, N)
+        ok = n - 1 > m
+        n, m = n[ok], m[ok]
+        u = lambda x: x.astype(np.uint32)
+        s_nm, s_up, s_left = t.S_batch(u(n), u(m)), t.S_batch(u(n - 1), u(m)), t.S_batch(u(n - 1), u(m - 1))
+        rhs = np.logaddexp(np.log(n - 1 - m * a) + s_up, s_left)
+        assert np.all(np.abs(s_nm - rhs) <= 1e-12 * np.maximum(1.0, np.abs(rhs))), np.max(np.abs(s_nm - rhs) / np.maximum(1.0, np.abs(rhs)))
+        v_nm, v_up, v_left = t.V_batch(u(n), u(m)), t.V_batch(u(n - 1), u(m)), t.V_batch(u(n - 1), u(m - 1))
+        k = m > 2  # V^n_2 has its own form (no column 1 in the V table)
+        rhs_v = (1 + (n - 1 - m * a) * v_up) / (1 / v_left + (n - 1 - (m - 1) * a))
+        assert np.all(np.abs(v_nm[k] - rhs_v[k]) <= 1e-12 * np.abs(rhs_v[k])), np.max(np.abs(v_nm[k] - rhs_v[k]) / np.abs(rhs_v[k]))
+    t.free()
