@@ -27,10 +27,16 @@ extern "C" {
  */
 int stb_S_batch(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out, size_t count);
 int stb_V_batch(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out, size_t count);
+/* S_U / S_UV (lib/stable.c:875-897) from the V table in the same kernel: U = n - m a + 1/V (m == 1: n - a;
+ * m == 0: NaN, the scalar call exits), UV = (n - m a) V + 1 (m == 1: -inf, m == n+1: 1, m == n: (n+1)/(n-1)) */
+int stb_U_batch(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out, size_t count);
+int stb_UV_batch(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out, size_t count);
 
 /* same, n/m/out are DEVICE pointers on the table's device; no growth is attempted */
 int stb_S_batch_device(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out, size_t count);
 int stb_V_batch_device(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out, size_t count);
+int stb_U_batch_device(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out, size_t count);
+int stb_UV_batch_device(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out, size_t count);
 
 /*
  * Grow the filled extent to at least n<=N, m<=M (within maxN/maxM) -- the exported form of

@@ -44,10 +44,10 @@ def lib() -> C.CDLL:
         f.restype, f.argtypes = d, [vp, u, u]
     L.S_S1.restype, L.S_S1.argtypes = d, [vp, u]
     L.S_report.restype, L.S_report.argtypes = None, [vp, vp]
-    for name in ("stb_S_batch", "stb_V_batch"):
+    for name in ("stb_S_batch", "stb_V_batch", "stb_U_batch", "stb_UV_batch"):
         f = getattr(L, name)
         f.restype, f.argtypes = C.c_int, [vp, u32p, u32p, dp, C.c_size_t]
-    for name in ("stb_S_batch_device", "stb_V_batch_device"):
+    for name in ("stb_S_batch_device", "stb_V_batch_device", "stb_U_batch_device", "stb_UV_batch_device"):
         f = getattr(L, name)
         f.restype, f.argtypes = C.c_int, [vp, vp, vp, vp, C.c_size_t]
     L.stb_extend.restype, L.stb_extend.argtypes = C.c_int, [vp, u, u]
@@ -181,6 +181,8 @@ class Table:
 
     def S_batch(self, n, m): return self._batch(self._L.stb_S_batch, n, m)
     def V_batch(self, n, m): return self._batch(self._L.stb_V_batch, n, m)
+    def U_batch(self, n, m): return self._batch(self._L.stb_U_batch, n, m)
+    def UV_batch(self, n, m): return self._batch(self._L.stb_UV_batch, n, m)
 
     def rows(self, which_V, n0, nrows):
         """Rows n0..n0+nrows-1 as an (nrows, ld) float64 array; column j holds m=j+1."""

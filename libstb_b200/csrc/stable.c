@@ -495,7 +495,7 @@ static int batch(stable_t *sp, int which, const uint32_t *n, const uint32_t *m, 
                  int on_device) {
   if (!sp || !sp->impl) return 1;
   if (which == STB_TAB_S && !(sp->flags & S_STABLE)) return 1;
-  if (which == STB_TAB_V && !(sp->flags & S_UVTABLE)) return 1;
+  if (which != STB_TAB_S && !(sp->flags & S_UVTABLE)) return 1;
   if (!on_device) {
     /* grow once to cover the whole batch, like the scalar calls would one by one */
     unsigned maxn = 0, maxm = 0;
@@ -509,7 +509,7 @@ static int batch(stable_t *sp, int which, const uint32_t *n, const uint32_t *m, 
     if (maxn > sp->usedN || maxm > sp->usedM)
       if (extend(sp, maxn > sp->usedN ? maxn : sp->usedN, maxm > sp->usedM ? maxm : sp->usedM)) return 1;
   }
-  return stb_cuda_gather(sp->impl->dev, which, sp->usedN, sp->usedM, n, m, out, count, on_device);
+  return stb_cuda_gather(sp->impl->dev, which, sp->a, sp->usedN, sp->usedM, n, m, out, count, on_device);
 }
 
 int stb_S_batch(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out, size_t count) {
@@ -517,6 +517,18 @@ int stb_S_batch(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out,
 }
 int stb_V_batch(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out, size_t count) {
   return batch(sp, STB_TAB_V, n, m, out, count, 0);
+}
+int stb_U_batch(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out, size_t count) {
+  return batch(sp, STB_GATHER_U, n, m, out, count, 0);
+}
+int stb_UV_batch(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out, size_t count) {
+  return batch(sp, STB_GATHER_UV, n, m, out, count, 0);
+}
+int stb_U_batch_device(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out, size_t count) {
+  return batch(sp, STB_GATHER_U, n, m, out, count, 1);
+}
+int stb_UV_batch_device(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out, size_t count) {
+  return batch(sp, STB_GATHER_UV, n, m, out, count, 1);
 }
 int stb_S_batch_device(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out, size_t count) {
   return batch(sp, STB_TAB_S, n, m, out, count, 1);

@@ -271,28 +271,44 @@ extern "C" int stb_cuda_read_rows(stb_dev_t *d, int which, unsigned row0, unsign
  *   V: m<2 or n<m -> 0, else the cell.
  * Anything outside the filled extent answers like "beyond bounds" (-inf / 0).
  */
+/* what: STB_TAB_S, STB_TAB_V, or the ratios derived from V: STB_GATHER_U = n - m a + 1/V (m == 1: n - a,
+ * lib/stable.c:875-883), STB_GATHER_UV = (n - m a) V + 1 (m == 1: -inf, m == n+1: 1, m == n: (n+1)/(n-1),
+ * lib/stable.c:885-897); m == 0 answers NaN for U (the scalar call exits) */
 template <typename T>
-__global__ void gather_kernel(const T *__restrict__ tab, size_t ld, int is_V, unsigned usedN, unsigned usedM,
+__global__ void gather_kernel(const T *__restrict__ tab, size_t ld, int what, double a, unsigned usedN, unsigned usedM,
                               const uint32_t *__restrict__ n, const uint32_t *__restrict__ m,
                               double *__restrict__ out, size_t count) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   const unsigned nn = n[i], mm = m[i];
   double v;
-  if (is_V) {
-    v = (mm < 2 || nn < mm || nn > usedN || mm > usedM) ? 0.0 : (double)tab[(size_t)(nn - 1) * ld + (mm - 1)];
-  } else {
+  if (what == STB_TAB_S) {
     if (nn == mm)
       v = 0.0;
     else if (mm == 0 || nn < mm || nn > usedN || mm > usedM)
       v = -HUGE_VAL;
     else
       v = (double)tab[(size_t)(nn - 1) * ld + (mm - 1)];
+  } else {
+    const double V = (mm < 2 || nn < mm || nn > usedN || mm > usedM) ? 0.0 : (double)tab[(size_t)(nn - 1) * ld + (mm - 1)];
+    if (what == STB_TAB_V)
+      v = V;
+    else {
+      // the scalar calls' arithmetic, operation by operation (no FMA contraction): bit-identical to S_U / S_UV
+      const double nd = (double)nn, nma = __dsub_rn(nd, __dmul_rn((double)mm, a));
+      if (what == STB_GATHER_U)
+        v = mm == 1 ? __dsub_rn(nd, a) : (mm == 0 ? nan("") : __dadd_rn(nma, __ddiv_rn(1.0, V)));
+      else
+        v = mm == 1 ? -HUGE_VAL
+                    : (mm == nn + 1 ? 1.0
+                                    : (mm == nn ? __ddiv_rn(__dadd_rn(nd, 1.0), __dsub_rn(nd, 1.0))
+                                                : __dadd_rn(__dmul_rn(nma, V), 1.0)));
+    }
   }
   out[i] = v;
 }
 
-extern "C" int stb_cuda_gather(stb_dev_t *d, int which, unsigned usedN, unsigned usedM, const uint32_t *n,
+extern "C" int stb_cuda_gather(stb_dev_t *d, int which, double a, unsigned usedN, unsigned usedM, const uint32_t *n,
                                const uint32_t *m, double *out, size_t count, int on_device) {
   CK(cudaSetDevice(d->device));
   const void *tab = which == STB_TAB_S ? d->S : d->V;
@@ -324,11 +340,11 @@ extern "C" int stb_cuda_gather(stb_dev_t *d, int which, unsigned usedN, unsigned
   }
   unsigned blocks = (unsigned)((count + 255) / 256);
   if (d->is_float)
-    gather_kernel<float><<<blocks, 256, 0, d->stream>>>((const float *)tab, d->ld, which == STB_TAB_V, usedN,
-                                                        usedM, dn, dm, dout, count);
+    gather_kernel<float><<<blocks, 256, 0, d->stream>>>((const float *)tab, d->ld, which, a, usedN, usedM, dn, dm, dout,
+                                                        count);
   else
-    gather_kernel<double><<<blocks, 256, 0, d->stream>>>((const double *)tab, d->ld, which == STB_TAB_V, usedN,
-                                                         usedM, dn, dm, dout, count);
+    gather_kernel<double><<<blocks, 256, 0, d->stream>>>((const double *)tab, d->ld, which, a, usedN, usedM, dn, dm,
+                                                         dout, count);
   CK(cudaGetLastError());
   if (!on_device)
     CK(cudaMemcpyAsync(out, d->g_out, count * sizeof(double), cudaMemcpyDeviceToHost, d->stream));

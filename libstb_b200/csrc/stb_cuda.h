@@ -76,8 +76,11 @@ int stb_cuda_read_rows(stb_dev_t *d, int which, unsigned row0, unsigned nrows, d
  * beyond usedN/usedM answer -inf / 0 (the C layer grows the table first when it may).
  * n, m, out are HOST pointers when on_device==0 (staged) or DEVICE pointers otherwise.
  */
-int stb_cuda_gather(stb_dev_t *d, int which, unsigned usedN, unsigned usedM, const uint32_t *n,
+int stb_cuda_gather(stb_dev_t *d, int which, double a, unsigned usedN, unsigned usedM, const uint32_t *n,
                     const uint32_t *m, double *out, size_t count, int on_device);
+/* `which` values beyond the two tables: ratios computed from V in the same kernel (a: the discount) */
+#define STB_GATHER_U 2
+#define STB_GATHER_UV 3
 
 /*
  * Discount sweep: fill MANY tables of one extent (N x M, log S only), one per discount, and keep

@@ -325,3 +325,21 @@ def test_concurrent_lookups_with_growth_S_THREADS():
     assert not errs, errs[:3]
     assert t.usedN > N0 and t.usedM > M0
     t.free()
+
+
+def test_batched_U_and_UV_match_the_scalar_calls():
+    """stb_U_batch / stb_UV_batch (one gather kernel on the V table) against S_U / S_UV, including
+    their special cases (lib/stable.c:875-897): m == 1, m == n, m == n + 1"""
+    N, M, a = 900, 120, 0.4
+    t = stb.Table(N, M, N, M, a, FLAGS)
+    rng = np.random.default_rng(8)
+    n = rng.integers(3, N - 2, size=3000).astype(np.uint32)
+    m = np.minimum(rng.integers(1, M - 2, size=3000), n).astype(np.uint32)
+    n[:4], m[:4] = [50, 60, 70, 80], [1, 60, 71, 2]  # m == 1, m == n, m == n + 1, m == 2
+    U, UV = t.U_batch(n, m), t.UV_batch(n, m)
+    for i in range(len(n)):
+        ni, mi = int(n[i]), int(m[i])
+        if mi <= ni:
+            assert U[i] == t.U(ni, mi), (ni, mi)
+        assert UV[i] == t.UV(ni, mi), (ni, mi)
+    t.free()
