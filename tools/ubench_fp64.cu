@@ -7,7 +7,8 @@
 template <int MODE>
 __global__ void k(double *out, long long *cyc, double a, double b, int iters) {
   double x[16];
-  for (int i = 0; i < 16; i++) x[i] = a + i;
+  unsigned y[16];
+  for (int i = 0; i < 16; i++) x[i] = a + i, y[i] = threadIdx.x + i;
   __syncthreads();
   long long t0 = clock64();
   for (int it = 0; it < iters; it++) {
@@ -16,13 +17,15 @@ __global__ void k(double *out, long long *cyc, double a, double b, int iters) {
       if (MODE == 0) x[i] = fma(x[i], b, a);
       if (MODE == 1) x[i] = x[i] + b;
       if (MODE == 2) x[i] = (i & 1) ? fma(x[i], b, a) : x[i] + b;
+      if (MODE == 5) { x[i] = fma(x[i], b, a); y[i] = y[i] * 1664525u + 1013904223u; }  // one DFMA + one IMAD, independent
+      if (MODE == 6) { y[i] = y[i] * 1664525u + 1013904223u; }                            // the IMAD alone
       if (MODE == 3) x[i] = (double)(__double2loint(x[i]) + it + i);  // I2F.F64.S32 (integer -> double conversion)
       if (MODE == 4) x[i] = __hiloint2double(0x43300000, __double2loint(x[i]) + it + i) - 4503601774854144.0;  // magic-number conversion: IADD + MOV + DADD
     }
   }
   long long t1 = clock64();
   double s = 0;
-  for (int i = 0; i < 16; i++) s += x[i];
+  for (int i = 0; i < 16; i++) s += x[i] + (double)y[i];
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
   if ((threadIdx.x & 31) == 0) cyc[blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32] = t1 - t0;
 }
@@ -49,6 +52,8 @@ int main() {
   for (int w : {1, 4, 8, 16, 32}) run<0>("DFMA", w);
   for (int w : {1, 4, 8, 16}) run<1>("DADD", w);
   for (int w : {1, 4, 16}) run<2>("DFMA+DADD", w);
+  for (int w : {1, 4, 16}) run<5>("DFMA+IMAD pair", w);
+  for (int w : {1, 4, 16}) run<6>("IMAD alone", w);
   for (int w : {1, 4, 16}) run<3>("I2F.F64", w);
   for (int w : {1, 4, 16}) run<4>("magic i2d", w);
   return 0;
