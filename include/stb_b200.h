@@ -67,7 +67,8 @@ stb_sweep_t *stb_sweep_create(unsigned N, unsigned M, uint32_t flags);
 int stb_sweep_set_pairs(stb_sweep_t *w, const uint32_t *n, const uint32_t *m, size_t npairs);
 int stb_sweep_run(stb_sweep_t *w, const double *a, size_t na, double *gather_out, double *sum_out,
                   double *lastrow_out);
-/* device milliseconds the fill kernels of the most recent stb_sweep_run took; tables filled per launch */
+/* device milliseconds of the most recent stb_sweep_run (CUDA events around its queue of fills and
+ * reductions: the fills are > 99 % of it); tables filled per launch */
 double stb_sweep_last_fill_ms(const stb_sweep_t *w);
 int stb_sweep_tables_in_flight(const stb_sweep_t *w);
 void stb_sweep_free(stb_sweep_t *w);

@@ -1001,6 +1001,11 @@ struct StripFillArgs {
   size_t ld;
   unsigned N, M;
   int num_sms;
+  // NULL: strip_fill waits for the fill and checks the watchdog flag itself.  Otherwise (PINNED host
+  // int, and only when the fill is a single launch) the launch is left in flight: the flag is copied
+  // there asynchronously and the caller checks it after its own synchronisation -- a sweep queues
+  // wave after wave without a host round trip per wave.
+  int *async_flag;
 };
 
 /*
@@ -1113,6 +1118,10 @@ inline int strip_fill(StripState *st, const StripFillArgs &A, cudaStream_t strea
       // the abort flag is checked per launch: a later memset must not hide it
       int flag = 0;
       if (last_launch) cudaEventRecord(ev_end, stream);
+      if (A.async_flag && A.ntables <= per_launch && passes == 1) {
+        e = cudaMemcpyAsync(A.async_flag, P.abort_flag, sizeof(int), cudaMemcpyDeviceToHost, stream);
+        break;
+      }
       e = cudaMemcpyAsync(&flag, P.abort_flag, sizeof(int), cudaMemcpyDeviceToHost, stream);
       if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
 #ifdef STB_PROFILE_PRODUCER

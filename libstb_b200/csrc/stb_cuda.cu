@@ -220,6 +220,7 @@ extern "C" int stb_cuda_fill(stb_dev_t *d, double a, unsigned startN, unsigned s
     args.N = N;
     args.M = M;
     args.num_sms = d->num_sms;
+    args.async_flag = NULL;
     rc = stb::strip_fill(&d->strip, args, d->stream, d->ev1, g_err, sizeof g_err);
   }
   if (rc) return rc;
@@ -370,8 +371,10 @@ struct stb_sweep_dev {
   size_t npairs, pairs_cap, gather_cap;
   double *d_gather;    // [T][npairs], allocated when a gather is first asked for
   double *d_partial;   // [T][nblk]
-  double *d_sum;       // [T]
-  double *h_stage;     // pinned staging for sums
+  double *d_sum;       // [stage_cap]: one sum per table of a run
+  double *h_stage;     // pinned staging for the sums of a whole run
+  int *h_flags;        // pinned: watchdog flag of every wave of a run
+  size_t stage_cap, flags_cap;
 };
 
 /* S_S conventions (lib/stable.c:941-949) on a dense slab; partial sums per block in a fixed order */
@@ -429,6 +432,7 @@ extern "C" void stb_cuda_sweep_destroy(stb_sweep_dev_t *w) {
   cudaFree(w->d_partial);
   cudaFree(w->d_sum);
   if (w->h_stage) cudaFreeHost(w->h_stage);
+  if (w->h_flags) cudaFreeHost(w->h_flags);
   stb::strip_state_free(&w->strip);
   if (w->ev0) cudaEventDestroy(w->ev0);
   if (w->ev1) cudaEventDestroy(w->ev1);
@@ -468,6 +472,7 @@ extern "C" stb_sweep_dev_t *stb_cuda_sweep_create(unsigned N, unsigned M, int is
   if (e == cudaSuccess) e = cudaMalloc(&w->s1, (size_t)w->T * N * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&w->d_sum, (size_t)w->T * sizeof(double));
   if (e == cudaSuccess) e = cudaHostAlloc(&w->h_stage, (size_t)w->T * sizeof(double), cudaHostAllocDefault);
+  if (e == cudaSuccess) w->stage_cap = (size_t)w->T;
   if (e != cudaSuccess) {
     fail(e, "stb_cuda_sweep_create");
     stb_cuda_sweep_destroy(w);
@@ -507,11 +512,12 @@ extern "C" int stb_cuda_sweep_run(stb_sweep_dev_t *w, const double *a, size_t na
   const size_t es = w->is_float ? 4 : 8;
   const size_t slab_elems = (size_t)w->N * w->ld;
   const int nblk = (int)((w->npairs + 255) / 256);
-  float total_ms = 0.f;
   if ((gather_out || sum_out) && !w->npairs) {
     snprintf(g_err, sizeof g_err, "stb_cuda_sweep_run: no look-up pairs set");
     return -1;
   }
+  if (fill_ms) *fill_ms = 0.f;
+  if (!na) return 0;
   if (gather_out && w->npairs > w->gather_cap) {
     cudaFree(w->d_gather);
     w->d_gather = NULL;
@@ -519,8 +525,34 @@ extern "C" int stb_cuda_sweep_run(stb_sweep_dev_t *w, const double *a, size_t na
     CK(cudaMalloc(&w->d_gather, (size_t)w->T * w->npairs * sizeof(double)));
     w->gather_cap = w->npairs;
   }
+  // The waves (T tables each, streamed through the same slabs) are queued back to back: stream order
+  // keeps fill -> reduce -> next fill apart, the per-table sums of the whole run collect in d_sum and
+  // come back with ONE copy, the watchdog flags of all waves in pinned memory, and the host waits once.
+  // (A wave whose results go to pageable caller memory -- gather_out, lastrow_out -- still waits for
+  // its own copies.)
+  const size_t nwaves = (na + (size_t)w->T - 1) / (size_t)w->T;
+  if (sum_out && na > w->stage_cap) {
+    cudaFree(w->d_sum);
+    cudaFreeHost(w->h_stage);
+    w->d_sum = NULL;
+    w->h_stage = NULL;
+    w->stage_cap = 0;
+    CK(cudaMalloc(&w->d_sum, na * sizeof(double)));
+    CK(cudaHostAlloc(&w->h_stage, na * sizeof(double), cudaHostAllocDefault));
+    w->stage_cap = na;
+  }
+  if (nwaves > w->flags_cap) {
+    if (w->h_flags) cudaFreeHost(w->h_flags);
+    w->h_flags = NULL;
+    w->flags_cap = 0;
+    CK(cudaHostAlloc(&w->h_flags, nwaves * sizeof(int), cudaHostAllocDefault));
+    w->flags_cap = nwaves;
+  }
+  memset(w->h_flags, 0, nwaves * sizeof(int));
   std::vector<stb::StripTable> tabs((size_t)w->T);
-  for (size_t j0 = 0; j0 < na; j0 += (size_t)w->T) {
+  CK(cudaEventRecord(w->ev0, w->stream));
+  size_t wave = 0;
+  for (size_t j0 = 0; j0 < na; j0 += (size_t)w->T, ++wave) {
     const int nt = (int)((na - j0 < (size_t)w->T) ? na - j0 : (size_t)w->T);
     for (int t = 0; t < nt; t++) {
       tabs[t].tabS = (char *)w->slab + (size_t)t * slab_elems * es;
@@ -538,12 +570,9 @@ extern "C" int stb_cuda_sweep_run(stb_sweep_dev_t *w, const double *a, size_t na
     args.N = w->N;
     args.M = w->M;
     args.num_sms = w->num_sms;
-    CK(cudaEventRecord(w->ev0, w->stream));
+    args.async_flag = w->h_flags + wave;
     int rc = stb::strip_fill(&w->strip, args, w->stream, w->ev1, g_err, sizeof g_err);
     if (rc) return rc;
-    float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, w->ev0, w->ev1));
-    total_ms += ms;
     if (gather_out || sum_out) {
       dim3 grid((unsigned)nblk, (unsigned)nt);
       if (w->is_float)
@@ -556,13 +585,14 @@ extern "C" int stb_cuda_sweep_run(stb_sweep_dev_t *w, const double *a, size_t na
                                                                    gather_out ? w->d_gather : NULL, w->d_partial);
       CK(cudaGetLastError());
       if (sum_out) {
-        sweep_sum_kernel<<<nt, 256, 0, w->stream>>>(w->d_partial, nblk, w->d_sum);
+        sweep_sum_kernel<<<nt, 256, 0, w->stream>>>(w->d_partial, nblk, w->d_sum + j0);
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(w->h_stage, w->d_sum, (size_t)nt * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
       }
-      if (gather_out)
+      if (gather_out) {
         CK(cudaMemcpyAsync(gather_out + j0 * w->npairs, w->d_gather, (size_t)nt * w->npairs * sizeof(double),
                            cudaMemcpyDeviceToHost, w->stream));
+        CK(cudaStreamSynchronize(w->stream));
+      }
     }
     if (lastrow_out) {
       for (int t = 0; t < nt; t++) {
@@ -577,12 +607,20 @@ extern "C" int stb_cuda_sweep_run(stb_sweep_dev_t *w, const double *a, size_t na
           for (unsigned c = 0; c < w->M; c++) lastrow_out[(j0 + t) * w->M + c] = (double)tmp[c];
         }
       }
+      CK(cudaStreamSynchronize(w->stream));
     }
-    CK(cudaStreamSynchronize(w->stream));
-    if (sum_out)
-      for (int t = 0; t < nt; t++) sum_out[j0 + t] = w->h_stage[t];
   }
-  if (fill_ms) *fill_ms = total_ms;
+  CK(cudaEventRecord(w->ev1, w->stream));
+  if (sum_out) CK(cudaMemcpyAsync(w->h_stage, w->d_sum, na * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
+  CK(cudaStreamSynchronize(w->stream));
+  for (size_t i = 0; i < nwaves; i++)
+    if (w->h_flags[i]) {
+      snprintf(g_err, sizeof g_err, "stb_cuda_sweep_run: pipeline watchdog fired in wave %zu of %zu", i, nwaves);
+      return -2;
+    }
+  if (sum_out)
+    for (size_t j = 0; j < na; j++) sum_out[j] = w->h_stage[j];
+  if (fill_ms) CK(cudaEventElapsedTime(fill_ms, w->ev0, w->ev1));
   return 0;
 }
 
