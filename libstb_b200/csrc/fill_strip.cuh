@@ -275,20 +275,24 @@ __device__ __forceinline__ void sts_s32_if(unsigned a, int v, bool pred) {
  * x ring; lane 0 reads the boundary ring instead -- by ONE load issued at the top of step i and
  * first used at the bottom of step i (yin for step i+1), so that its latency hides behind the
  * step's own arithmetic: the row-to-row critical path is the DFMA, nothing else.  nb_addr is the
- * address of the next such load and advances by nb_stride (a ring row / one boundary entry);
- * the first step of a batch gets the value in nb0 (the batch set-up fetches it after the
- * renormalisation).  Everything is stored unconditionally: rows that do not exist (before the
+ * address of the next such load and advances by nb_stride (a ring row / one boundary entry).
+ * The first step of a batch reads the LAST row of the previous batch (first_addr), whose values
+ * are still in the neighbour's old units: scn0 = (old neighbour units -> old own units) x (own
+ * rescale), a product of two powers of two, converts them exactly.  Everything is stored unconditionally: rows that do not exist (before the
  * strip's first row, past N) land in ring slots the consumers never read as valid.
  */
 template <int K, bool HAS_V, bool DUP, int CP, int RS, bool FIRST>
 __device__ __forceinline__ void strip_steps(double (&x)[K], const double (&ma)[K], double &nm1, double &yin,
-                                            const double nb0, const double scn, unsigned &nb_addr,
+                                            const unsigned first_addr, const double scn0, const double scn,
+                                            unsigned &nb_addr,
                                             const unsigned nb_stride, const bool write_out, const unsigned xr,
                                             const unsigned yr, const unsigned outp) {
 #pragma unroll
   for (int i = 0; i < ST_RB; i++) {
-    double nb = nb0;
-    if (!(FIRST && i == 0)) {
+    double nb;
+    if (FIRST && i == 0)
+      nb = lds_f64(first_addr);
+    else {
       nb = lds_f64(nb_addr);
       nb_addr += nb_stride;
     }
@@ -310,7 +314,7 @@ __device__ __forceinline__ void strip_steps(double (&x)[K], const double (&ma)[K
     sts_f64(xr + (i * CP + K - 1) * 8, x[K - 1]);
     if (DUP) sts_f64(xr + ((RS + i) * CP + K - 1) * 8, x[K - 1]);
     sts_f64_if(outp + i * 8, x[K - 1], write_out);
-    yin = nb * scn;
+    yin = nb * ((FIRST && i == 0) ? scn0 : scn);
     if (HAS_V) {
       sts_f64(yr + i * 32 * 8, yin);
       if (DUP) sts_f64(yr + (RS + i) * 32 * 8, yin);
@@ -392,8 +396,10 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
   long long E = 0;
   int elow = 0;
   int e_n = 0, elow_n = 0, sE_n = 0;  // predicted for the next batch: exponent step, E, neighbour's E
-  double sc_n = 1.0;
+  double sc_n = 1.0, scn_prev = 0.0;
   asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a_er), "r"(0x80000000u - 1023u));
+  // batch 0 reads "the previous batch's last row": zeros
+  sts_f64(a_xr + ((RS - 1) * CP + K - 1) * 8, 0.0);
 
   int cvalid_p = P.M - g.rs;
   if (cvalid_p > P.C) cvalid_p = P.C;
@@ -439,18 +445,20 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
     const unsigned outp = a_out_x + os * (ST_B * 8);
     const unsigned xr = a_xr + s0 * (ST_RB * CP * 8);
     const unsigned yr = a_yr + (HAS_V ? s0 * (ST_RB * 32 * 8) : 0);
-    // the neighbour's value for the first step, in the new units
-    double nb0 = shfl_up_d(x[K - 1]);
-    if (lane0) nb0 = lds_f64(bnd);
+    // the first step reads the previous batch's last row (lane 0: this batch's first boundary entry)
+    const unsigned first_addr = lane0 ? bnd : a_xr + ((s0 == 0 ? RS : s0 * ST_RB) - 1) * (CP * 8) - 8u;
+    const double scn0 = lane0 ? scn : scn_prev * sc_n;
+    scn_prev = scn;
     unsigned nb_addr = lane0 ? bnd + 8u : xr - 8u;
 
     ST_TICK(tk3);
     // ---- sixteen steps, eight per consumer slot; only ring rows 0..7 have duplicates ----
     if (s0 == 0)
-      strip_steps<K, HAS_V, true, CP, RS, true>(x, ma, nm1, yin, nb0, scn, nb_addr, nb_stride, write_out, xr, yr, outp);
+      strip_steps<K, HAS_V, true, CP, RS, true>(x, ma, nm1, yin, first_addr, scn0, scn, nb_addr, nb_stride, write_out, xr,
+                                                yr, outp);
     else
-      strip_steps<K, HAS_V, false, CP, RS, true>(x, ma, nm1, yin, nb0, scn, nb_addr, nb_stride, write_out, xr, yr,
-                                                 outp);
+      strip_steps<K, HAS_V, false, CP, RS, true>(x, ma, nm1, yin, first_addr, scn0, scn, nb_addr, nb_stride, write_out,
+                                                 xr, yr, outp);
     // mid-batch: fetch the words the NEXT batch's flow control will look at, fix the next scale
     {
       int s1 = s0 + 2;
@@ -467,7 +475,7 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
       asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a_er + (((p + 1) & (ST_NJ - 1)) * 32) * 4),
                    "r"((unsigned)elow_n + (0x80000000u - 1023u)));
     }
-    strip_steps<K, HAS_V, false, CP, RS, false>(x, ma, nm1, yin, 0.0, scn, nb_addr, nb_stride, write_out,
+    strip_steps<K, HAS_V, false, CP, RS, false>(x, ma, nm1, yin, 0u, scn, scn, nb_addr, nb_stride, write_out,
                                                 xr + ST_RB * CP * 8, yr + (HAS_V ? ST_RB * 32 * 8 : 0),
                                                 outp + ST_RB * 8);
     ST_TICK(tk4);

@@ -43,10 +43,9 @@ __global__ void __launch_bounds__(512, 1) kern(long long *cycles, double *sink, 
       int sE = __shfl_up_sync(0xffffffffu, elow, 1);
       if (lane == 0) sE = elow;
       const double scn = lane == 0 ? 0.0 : pow2i(sE - elow);
-      double nb0 = shfl_up_d(x[K - 1]);
       unsigned nb_addr = lane == 0 ? a_out + 8u : a_xr - 8u;
-      strip_steps<K, false, false, CP, RS, true>(x, ma, nm1, yin, nb0, scn, nb_addr, nb_stride, lane == 31, a_xr, a_yr, a_out);
-      strip_steps<K, false, false, CP, RS, false>(x, ma, nm1, yin, 0.0, scn, nb_addr, nb_stride, lane == 31, a_xr + 8 * CP * 8,
+      strip_steps<K, false, false, CP, RS, true>(x, ma, nm1, yin, lane == 0 ? a_out : a_xr + 15 * CP * 8 - 8u, scn, scn, nb_addr, nb_stride, lane == 31, a_xr, a_yr, a_out);
+      strip_steps<K, false, false, CP, RS, false>(x, ma, nm1, yin, 0u, scn, scn, nb_addr, nb_stride, lane == 31, a_xr + 8 * CP * 8,
                                                   a_yr, a_out + 64);
     }
     long long t1 = clock64();

@@ -64,14 +64,12 @@ __global__ void steps_kernel(long long *cycles, double *sink, int batches, doubl
     int sE = __shfl_up_sync(0xffffffffu, elow, 1);
     if (lane == 0) sE = elow;
     const double scn = lane == 0 ? 0.0 : pow2i(sE - elow);
-    double nb0 = shfl_up_d(x[K - 1]);
     unsigned nb_addr = lane == 0 ? a_out + 8u : a_xr - 8u;
     if (MODE == 0) {
-      strip_steps<K, false, false, CP, RS, true>(x, ma, nm1, yin, nb0, scn, nb_addr, nb_stride, lane == 31, a_xr, a_yr, a_out);
-      strip_steps<K, false, false, CP, RS, false>(x, ma, nm1, yin, 0.0, scn, nb_addr, nb_stride, lane == 31, a_xr + 8 * CP * 8,
+      strip_steps<K, false, false, CP, RS, true>(x, ma, nm1, yin, lane == 0 ? a_out : a_xr + 15 * CP * 8 - 8u, scn, scn, nb_addr, nb_stride, lane == 31, a_xr, a_yr, a_out);
+      strip_steps<K, false, false, CP, RS, false>(x, ma, nm1, yin, 0u, scn, scn, nb_addr, nb_stride, lane == 31, a_xr + 8 * CP * 8,
                                                   a_yr, a_out + 64);
     } else {
-      yin = nb0 * scn;
       steps_var<K, CP, MODE>(x, ma, nm1, yin, scn, nb_addr, nb_stride, a_xr);
       steps_var<K, CP, MODE>(x, ma, nm1, yin, scn, nb_addr, nb_stride, a_xr + 8 * CP * 8);
     }
