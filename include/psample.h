@@ -66,6 +66,23 @@ double samplea(double apar, int I, int *K, scnt_int *T, scnt_int **n, stcnt_int 
                void (*getval)(scnt_int *n, stcnt_int *t, unsigned i, unsigned k), double *bpar, rngp_t rng,
                int loops, int verbose);
 
+/*
+ * The table-free discount update (lib/samplea.c:227-341; compiled in the reference only with
+ * SAMPLEA_M, lib/psample.h:30).  S: the caller's table at the current discount mya.  For every node
+ * with 1 < t < n the sizes of its t tables are sampled given (n, t) -- one uniform per node, in
+ * (i,k) order, from rng -- through ratios of S_S values (here: one kernel over all nodes,
+ * stb_partition_sample); given the sizes the posterior of a needs no Stirling numbers, and one
+ * slice-sampling (or ARS) step over it returns the new discount.  n and t must be arrays (the
+ * partition step does not use getval, like the reference).
+ * Deviation: in the reference's ARS build this function hands arms_simple a NULL data pointer
+ * (lib/samplea.c:323-324) and would crash; here the ARS mode passes the statistics.
+ */
+double samplea2(double mya, stable_t *S, int I, int *K, scnt_int *T, scnt_int **n, stcnt_int **t,
+                void (*getval)(scnt_int *n, stcnt_int *t, unsigned i, unsigned k), double *bpar, rngp_t rng,
+                int loops, int verbose);
+/* log(exp(x) - exp(y)), -inf when y >= x (lib/samplea.c:229-239) */
+double logminus(double x, double y);
+
 /* ------------------------------------------------------------------------------------------ */
 /* batched samplers: C independent chains in lock-step, one batched evaluation per round        */
 /* ------------------------------------------------------------------------------------------ */

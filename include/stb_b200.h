@@ -32,6 +32,28 @@ int stb_V_batch(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out,
 int stb_U_batch(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out, size_t count);
 int stb_UV_batch(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out, size_t count);
 
+/*
+ * The seat-partition sampler inside samplea2 (lib/samplea.c:290-321) for `count` nodes in one kernel, one
+ * thread per node: node j has n[j] customers at t[j] tables (1 < t[j] < n[j]); its t[j]-1 sampled table
+ * sizes are written at m_out[off[j] .. off[j]+t[j]-2], entry M-1 by round M = t-1 .. 1 (the last table's
+ * size is what remains).  a: the discount the table was filled at.
+ *   exact == 0 (STB_PARTITION_REFERENCE): the reference's arithmetic, operation by operation; logu[j] =
+ *     log of node j's ONE uniform.  As written there the remainder starts at S(n,t) + log u while the
+ *     terms are normalised by S(n,t), so beyond the smallest counts no walk stops early: the result is one
+ *     table of n-t+1 customers and t-1 singletons, whatever u.  Mirrored for parity with -DSAMPLEA_M builds.
+ *   exact != 0 (STB_PARTITION_EXACT): draws from P(l | N, M+1) = C(N-1,l-1) (1-a)_{l-1} S^{N-l}_M / S^N_{M+1},
+ *     the size of the table holding a given customer when N customers sit at M+1 tables, round by round;
+ *     logu has n_m entries, logu[off[j] + M-1] = log of the uniform of round M.
+ * The table is grown to cover the nodes first; counts beyond its maximum size are an error.  HOST
+ * pointers.  Returns non-zero on error.
+ */
+#define STB_PARTITION_REFERENCE 0
+#define STB_PARTITION_EXACT 1
+int stb_partition_sample(stable_t *sp, double a, const uint32_t *n, const uint16_t *t, const double *logu,
+                         const uint32_t *off, size_t count, uint16_t *m_out, size_t n_m, int exact);
+/* which of the two samplea2 uses (default STB_PARTITION_REFERENCE); returns the previous setting */
+int stb_set_partition_mode(int mode);
+
 /* same, n/m/out are DEVICE pointers on the table's device; no growth is attempted */
 int stb_S_batch_device(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out, size_t count);
 int stb_V_batch_device(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out, size_t count);

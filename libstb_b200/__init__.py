@@ -19,6 +19,8 @@ LIB_PATH = os.environ.get("STB_B200_LIB") or os.path.join(_HERE, "lib", "libstb_
 # flag bits, include/stable.h
 S_STABLE, S_UVTABLE, S_FLOAT, S_VERBOSE, S_QUITONBOUND, S_THREADS, S_ASYMPT = 1, 2, 4, 8, 16, 32, 64
 S_MIRROR_ORDER, S_NOMIRROR = 1 << 16, 1 << 17
+STB_SAMPLER_SLICE, STB_SAMPLER_ARS = 0, 1          # include/psample.h
+STB_PARTITION_REFERENCE, STB_PARTITION_EXACT = 0, 1  # include/stb_b200.h
 
 _lib = None
 
@@ -67,6 +69,14 @@ def lib() -> C.CDLL:
     L.samplea.restype = d
     L.samplea.argtypes = [d, C.c_int, ip, u32p, C.POINTER(u32p), C.POINTER(C.POINTER(C.c_uint16)), vp, dp, vp,
                           C.c_int, C.c_int]
+    L.samplea2.restype = d
+    L.samplea2.argtypes = [d, vp, C.c_int, ip, u32p, C.POINTER(u32p), C.POINTER(C.POINTER(C.c_uint16)), vp, dp, vp,
+                           C.c_int, C.c_int]
+    L.logminus.restype, L.logminus.argtypes = d, [d, d]
+    L.stb_partition_sample.restype = C.c_int
+    L.stb_partition_sample.argtypes = [vp, d, u32p, C.POINTER(C.c_uint16), dp, u32p, C.c_size_t,
+                                       C.POINTER(C.c_uint16), C.c_size_t, C.c_int]
+    L.stb_set_partition_mode.restype, L.stb_set_partition_mode.argtypes = C.c_int, [C.c_int]
     for name in ("gsl_rng_gaussian_ziggurat", "gsl_rng_gamma", "digammaRN", "MLdigamma", "MLtrigamma", "digammaInv",
                  "MLtetragamma", "MLpentagamma"):
         f = getattr(L, name)
@@ -183,6 +193,28 @@ class Table:
     def V_batch(self, n, m): return self._batch(self._L.stb_V_batch, n, m)
     def U_batch(self, n, m): return self._batch(self._L.stb_U_batch, n, m)
     def UV_batch(self, n, m): return self._batch(self._L.stb_UV_batch, n, m)
+
+    def partition_sample(self, a, n, t, logu, exact=False):
+        """stb_partition_sample: table sizes of nodes (n[j], t[j]), 1 < t < n.  logu: one log-uniform per node
+        (reference mode) or t[j]-1 per node laid out like the result (exact mode).  Returns (m, off):
+        node j's sizes are m[off[j] : off[j] + t[j] - 1], entry M-1 drawn by round M."""
+        n = np.ascontiguousarray(n, dtype=np.uint32)
+        t = np.ascontiguousarray(t, dtype=np.uint16)
+        logu = np.ascontiguousarray(logu, dtype=np.float64)
+        sizes = t.astype(np.int64) - 1
+        off = np.zeros(n.shape[0], dtype=np.uint32)
+        if n.shape[0]:
+            off[1:] = np.cumsum(sizes)[:-1]
+        n_m = int(sizes.sum())
+        if logu.shape[0] != (n_m if exact else n.shape[0]):
+            raise ValueError("logu: one entry per node (reference mode) or per sampled size (exact mode)")
+        m = np.zeros(max(n_m, 1), dtype=np.uint16)
+        u32p, u16p, dp = C.POINTER(C.c_uint32), C.POINTER(C.c_uint16), C.POINTER(C.c_double)
+        if self._L.stb_partition_sample(self.sp, float(a), n.ctypes.data_as(u32p), t.ctypes.data_as(u16p),
+                                        logu.ctypes.data_as(dp), off.ctypes.data_as(u32p), n.shape[0],
+                                        m.ctypes.data_as(u16p), n_m, int(bool(exact))):
+            raise RuntimeError("stb_partition_sample failed: " + self._L.stb_last_error().decode())
+        return m[:n_m], off
 
     def rows(self, which_V, n0, nrows):
         """Rows n0..n0+nrows-1 as an (nrows, ld) float64 array; column j holds m=j+1."""

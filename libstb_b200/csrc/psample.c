@@ -17,6 +17,7 @@
 
 #include "arms.h"
 #include "digamma.h"
+#include "lgamma.h"
 #include "psample.h"
 #include "rng48.h"
 #include "specfun.h"
@@ -357,5 +358,151 @@ double samplea(double mya, int I, int *K, scnt_int *T, scnt_int **n, stcnt_int *
   free(ald.nn);
   free(ald.tt);
   free(ald.val);
+  return mya;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* samplea2, lib/samplea.c:227-341 (SAMPLEA_M)                                                  */
+/* ------------------------------------------------------------------------------------------ */
+double logminus(double x, double y) { /* lib/samplea.c:229-239 */
+  if (y >= x) return -HUGE_VAL;
+  if (y - x < -80) return x - exp(y - x);
+  return x + log(1 - exp(y - x));
+}
+
+static int g_partition_mode = STB_PARTITION_REFERENCE;
+int stb_set_partition_mode(int mode) {
+  int old = g_partition_mode;
+  if (mode == STB_PARTITION_REFERENCE || mode == STB_PARTITION_EXACT) g_partition_mode = mode;
+  return old;
+}
+
+typedef struct {
+  int I;
+  int *K;
+  scnt_int *T;
+  scnt_int **n;
+  stcnt_int **t;
+  void (*val)(scnt_int *n, stcnt_int *t, unsigned i, unsigned k);
+  double *bpar;
+  stcnt_int *m; /* sampled table sizes, t-1 per node with 1 < t < n, in (i,k) order */
+} AL2Data;
+
+/* log p(a = x | table sizes) up to a constant, summed in the reference's order (lib/samplea.c:87-150) */
+static double aterms2(double x, void *mydata) {
+  AL2Data *mp = (AL2Data *)mydata;
+  double val = 0;
+  struct gcache_s lgp;
+  stcnt_int *mm = mp->m;
+  int i, k;
+  if (x <= 0) {
+    fprintf(stderr, "Illegal discount value in aterms2()\n");
+    exit(1);
+  }
+  gcache_init(&lgp, 1 - x);
+  for (i = 0; i < mp->I; i++) {
+    val += mp->T[i] * log(x) + lgamma(mp->T[i] + mp->bpar[i] / x) - lgamma(mp->bpar[i] / x);
+    for (k = 0; k < mp->K[i]; k++) {
+      scnt_int n;
+      stcnt_int t;
+      if (mp->val)
+        mp->val(&n, &t, i, k);
+      else {
+        n = mp->n[i][k];
+        t = mp->t[i][k];
+      }
+      if (n == 0 || t == n) continue;
+      if (t == 1)
+        val += gcache_value(&lgp, n - 1);
+      else {
+        int l;
+        for (l = t - 2; l >= 0; l--) {
+          if (mm[l] > 1) val += gcache_value(&lgp, mm[l] - 1);
+          n -= mm[l];
+        }
+        if (n > 0) val += gcache_value(&lgp, n - 1);
+        mm += t - 1;
+      }
+    }
+  }
+  return val;
+}
+
+double samplea2(double mya, stable_t *S, int I, int *K, scnt_int *T, scnt_int **n, stcnt_int **t,
+                void (*getval)(scnt_int *n, stcnt_int *t, unsigned i, unsigned k), double *bpar, rngp_t rng,
+                int loops, int verbose) {
+  double inita[3] = {A_MIN, 1, A_MAX};
+  int i, k;
+  size_t n_m = 0, cnt = 0, j = 0, o = 0;
+  const int exact = g_partition_mode == STB_PARTITION_EXACT;
+  AL2Data ald;
+  uint32_t *pn, *poff;
+  uint16_t *pt;
+  double *plogu;
+  (void)verbose;
+  inita[1] = mya;
+  if (fabs(inita[1] - A_MAX) / A_MAX < 0.00001) inita[1] = A_MAX * 0.999 + A_MIN * 0.001;
+  if (fabs(inita[1] - A_MIN) / A_MIN < 0.00001) inita[1] = A_MIN * 0.999 + A_MAX * 0.001;
+  if (inita[1] - SQUEEZEA > A_MIN) inita[0] = inita[1] - SQUEEZEA;
+  if (inita[1] + SQUEEZEA < A_MAX) inita[2] = inita[1] + SQUEEZEA;
+  ald.T = T;
+  ald.n = n;
+  ald.t = t;
+  ald.I = I;
+  ald.K = K;
+  ald.val = getval;
+  ald.bpar = bpar;
+  for (i = 0; i < I; i++)
+    for (k = 0; k < K[i]; k++)
+      if (t[i][k] > 1 && t[i][k] < n[i][k]) {
+        n_m += (size_t)t[i][k] - 1;
+        cnt++;
+      }
+  ald.m = (stcnt_int *)malloc(sizeof(*ald.m) * (n_m ? n_m : 1));
+  pn = (uint32_t *)malloc(sizeof(uint32_t) * (cnt ? cnt : 1));
+  poff = (uint32_t *)malloc(sizeof(uint32_t) * (cnt ? cnt : 1));
+  pt = (uint16_t *)malloc(sizeof(uint16_t) * (cnt ? cnt : 1));
+  plogu = (double *)malloc(sizeof(double) * (exact ? (n_m ? n_m : 1) : (cnt ? cnt : 1)));
+  if (!ald.m || !pn || !poff || !pt || !plogu) {
+    fprintf(stderr, "Out of memory for samplea()\n");
+    exit(1);
+  }
+  /* one uniform per node in (i,k) order (lib/samplea.c:293), then every node's walk in one kernel */
+  for (i = 0; i < I; i++)
+    for (k = 0; k < K[i]; k++)
+      if (t[i][k] > 1 && t[i][k] < n[i][k]) {
+        pn[j] = n[i][k];
+        pt[j] = t[i][k];
+        if (exact) { /* one uniform per round, M = t-1 .. 1 */
+          int M;
+          for (M = (int)t[i][k] - 1; M >= 1; M--) plogu[o + (size_t)M - 1] = log(rng_unit(rng));
+        } else
+          plogu[j] = log(rng_unit(rng));
+        poff[j] = (uint32_t)o;
+        o += (size_t)t[i][k] - 1;
+        j++;
+      }
+  if (cnt && stb_partition_sample(S, mya, pn, pt, plogu, poff, cnt, ald.m, n_m, exact)) {
+    fprintf(stderr, "samplea2: partition sampling failed: %s\n", stb_last_error());
+    exit(1);
+  }
+  free(pn);
+  free(poff);
+  free(pt);
+  free(plogu);
+  if (g_sampler == STB_SAMPLER_ARS) { /* lib/samplea.c:322-328, with the data pointer the reference forgets */
+    arms_simple(3, inita, inita + 2, aterms2, &ald, 0, inita + 1, &mya);
+    if (mya < inita[0] || mya > inita[2]) {
+      fprintf(stderr, "Arms_simple(apar) returned value out of bounds\n");
+      exit(1);
+    }
+  } else {
+    inita[1] = A_MAX;
+    if (SliceSimple(&mya, aterms2, inita, rng, loops, &ald)) {
+      fprintf(stderr, "SliceSimple error\n");
+      exit(1);
+    }
+  }
+  free(ald.m);
   return mya;
 }

@@ -537,6 +537,33 @@ int stb_V_batch_device(stable_t *sp, const uint32_t *n, const uint32_t *m, doubl
   return batch(sp, STB_TAB_V, n, m, out, count, 1);
 }
 
+/* samplea2's partition sampler over this table (stb_b200.h); lib/samplea.c:290-321 */
+int stb_partition_sample(stable_t *sp, double a, const uint32_t *n, const uint16_t *t, const double *logu,
+                         const uint32_t *off, size_t count, uint16_t *m_out, size_t n_m, int exact) {
+  unsigned maxn = 0, maxt = 0;
+  size_t i;
+  if (!sp || !sp->impl || !(sp->flags & S_STABLE)) {
+    stb_cuda_set_error("stb_partition_sample: no S table", 0);
+    return 1;
+  }
+  for (i = 0; i < count; i++) {
+    if (t[i] < 2 || t[i] >= n[i] || (size_t)off[i] + t[i] - 1 > n_m) {
+      stb_cuda_set_error("stb_partition_sample: node needs 1 < t < n and room for t-1 sizes", 0);
+      return 1;
+    }
+    if (n[i] > maxn) maxn = n[i];
+    if (t[i] > maxt) maxt = t[i];
+  }
+  if (maxn > sp->maxN || maxt > sp->maxM) {
+    /* S_S would answer -inf (or the asymptote) here and the reference would sample from garbage */
+    stb_cuda_set_error("stb_partition_sample: counts beyond the table's maximum size", 0);
+    return 1;
+  }
+  if (maxn > sp->usedN || maxt > sp->usedM)
+    if (extend(sp, maxn > sp->usedN ? maxn : sp->usedN, maxt > sp->usedM ? maxt : sp->usedM)) return 1;
+  return stb_cuda_partition(sp->impl->dev, a, n, t, logu, off, count, m_out, n_m, exact);
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* discount sweep (stb_b200.h)                                                                 */
 /* ------------------------------------------------------------------------------------------ */

@@ -354,6 +354,114 @@ extern "C" int stb_cuda_gather(stb_dev_t *d, int which, double a, unsigned usedN
 }
 
 // ---------------------------------------------------------------------------------------------
+// seat-partition sampler of samplea2 (lib/samplea.c:290-321)
+// ---------------------------------------------------------------------------------------------
+/* log(e^x - e^y), lib/samplea.c:233-239 */
+__device__ __forceinline__ double logminus_dev(double x, double y) {
+  if (y >= x) return -HUGE_VAL;
+  const double d = __dsub_rn(y, x);
+  if (d < -80.0) return __dsub_rn(x, exp(d));
+  return __dadd_rn(x, log(__dsub_rn(1.0, exp(d))));
+}
+
+/*
+ * One thread per node (n customers at t tables, 1 < t < n).  Round M = t-1 .. 1 draws the size l of
+ * one more table from the remaining N customers by walking l = 1, 2, ... and subtracting each
+ * term's mass from the running remainder.
+ *   exact == 0: the reference's loop, operation by operation (lib/samplea.c:293-314): ONE uniform per
+ *     node, rem = ptot + log u with ptot = S(n,t) never renewed, growth factor (l - a)(N-l+1)/(l-1).
+ *     Because ptot (a large log Stirling number) is added to the remainder while the terms are
+ *     normalised by it, no term reaches the remainder unless S(n,t) is tiny (n of a few units):
+ *     the walk runs to its end and the "sample" is one table of N-M customers and singletons.
+ *     Mirrored for parity.
+ *   exact != 0: the distribution the loop is after, P(l | N, M+1) = C(N-1,l-1) (1-a)_{l-1} S^{N-l}_M /
+ *     S^N_{M+1} (it sums to one by the recurrence of the generalised Stirling numbers): a fresh uniform
+ *     per round (logu[off + M-1]), rem = log u, the normaliser S(N, M+1) of the CURRENT N, growth
+ *     factor (l-1-a)(N-l+1)/(l-1).
+ * The walk is sequential, but the rounds of one node visit about n cells in total, so a node costs
+ * O(n) table reads; the table (a few MB for the samplers' sizes) stays in L2.
+ */
+template <typename T>
+__global__ void partition_kernel(const T *__restrict__ tab, const double *__restrict__ s1, size_t ld, double a,
+                                 const uint32_t *__restrict__ n, const uint16_t *__restrict__ t,
+                                 const double *__restrict__ logu, const uint32_t *__restrict__ off,
+                                 uint16_t *__restrict__ m, size_t count, int exact) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  int N = (int)n[i];
+  const int t0 = (int)t[i];
+  auto S = [&](int nn, int mm) -> double {  // S_S, lib/stable.c:941-974, inside the table
+    if (nn == mm) return 0.0;
+    if (mm == 1) return s1[nn - 1];
+    return (double)tab[(size_t)(nn - 1) * ld + (mm - 1)];
+  };
+  double ptot = S(N, t0);
+  double rem = exact ? 0.0 : __dadd_rn(ptot, logu[i]);
+  const double shift = exact ? 1.0 : 0.0;
+  uint16_t *mp = m + off[i];
+  for (int M = t0 - 1; M >= 1; M--) {
+    if (exact) {
+      ptot = S(N, M + 1);
+      rem = logu[off[i] + M - 1];
+    }
+    double fact = 0.0;
+    int l;
+    for (l = 1; l <= N - M; l++) {
+      if (l > 1)
+        fact = __dadd_rn(fact, log(__ddiv_rn(__dmul_rn(__dsub_rn((double)l - shift, a), (double)(N - l + 1)),
+                                             (double)(l - 1))));
+      const double term = __dsub_rn(__dadd_rn(fact, S(N - l, M)), ptot);
+      if (term >= rem) break;
+      rem = logminus_dev(rem, term);
+    }
+    if (l > N - M) l = N - M;
+    mp[M - 1] = (uint16_t)l;
+    N -= l;
+  }
+}
+
+extern "C" int stb_cuda_partition(stb_dev_t *d, double a, const uint32_t *n, const uint16_t *t, const double *logu,
+                                  const uint32_t *off, size_t count, uint16_t *m_out, size_t n_m, int exact) {
+  CK(cudaSetDevice(d->device));
+  if (!d->S || !d->s1) {
+    snprintf(g_err, sizeof g_err, "stb_cuda_partition: S table not held");
+    return -1;
+  }
+  if (count == 0 || n_m == 0) return 0;
+  // one staging block: n, off (u32), logu (f64), t (u16), m (u16)
+  const size_t b_n = count * sizeof(uint32_t), b_u = (exact ? n_m : count) * sizeof(double), b_t = count * sizeof(uint16_t),
+               b_m = n_m * sizeof(uint16_t);
+  const size_t o_u = 0, o_n = o_u + b_u, o_off = o_n + b_n, o_t = o_off + b_n, o_m = (o_t + b_t + 7) & ~(size_t)7;
+  char *buf = NULL;
+  CK(cudaMalloc(&buf, o_m + b_m));
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(buf + o_u, logu, b_u, cudaMemcpyHostToDevice, d->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(buf + o_n, n, b_n, cudaMemcpyHostToDevice, d->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(buf + o_off, off, b_n, cudaMemcpyHostToDevice, d->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(buf + o_t, t, b_t, cudaMemcpyHostToDevice, d->stream);
+  if (e == cudaSuccess) {
+    // 64 threads per block: nodes differ in length by orders of magnitude, small blocks spread the long ones
+    const unsigned blocks = (unsigned)((count + 63) / 64);
+    if (d->is_float)
+      partition_kernel<float><<<blocks, 64, 0, d->stream>>>((const float *)d->S, d->s1, d->ld, a,
+                                                            (const uint32_t *)(buf + o_n), (const uint16_t *)(buf + o_t),
+                                                            (const double *)(buf + o_u), (const uint32_t *)(buf + o_off),
+                                                            (uint16_t *)(buf + o_m), count, exact);
+    else
+      partition_kernel<double><<<blocks, 64, 0, d->stream>>>((const double *)d->S, d->s1, d->ld, a,
+                                                             (const uint32_t *)(buf + o_n), (const uint16_t *)(buf + o_t),
+                                                             (const double *)(buf + o_u), (const uint32_t *)(buf + o_off),
+                                                             (uint16_t *)(buf + o_m), count, exact);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(m_out, buf + o_m, b_m, cudaMemcpyDeviceToHost, d->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
+  cudaFree(buf);
+  if (e != cudaSuccess) return fail(e, "stb_cuda_partition");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // discount sweep
 // ---------------------------------------------------------------------------------------------
 struct stb_sweep_dev {

@@ -78,6 +78,14 @@ int stb_cuda_read_rows(stb_dev_t *d, int which, unsigned row0, unsigned nrows, d
  */
 int stb_cuda_gather(stb_dev_t *d, int which, double a, unsigned usedN, unsigned usedM, const uint32_t *n,
                     const uint32_t *m, double *out, size_t count, int on_device);
+/*
+ * samplea2's seat-partition sampler (lib/samplea.c:290-321) for `count` nodes at once: node j has
+ * n[j] customers at t[j] tables (1 < t < n, inside the filled table), logu[j] = log of its uniform
+ * draw (exact != 0: logu[off[j] + M-1] for round M, n_m entries), and writes its t[j]-1 table sizes at
+ * m_out[off[j] ..].  Host pointers.
+ */
+int stb_cuda_partition(stb_dev_t *d, double a, const uint32_t *n, const uint16_t *t, const double *logu,
+                       const uint32_t *off, size_t count, uint16_t *m_out, size_t n_m, int exact);
 /* `which` values beyond the two tables: ratios computed from V in the same kernel (a: the discount) */
 #define STB_GATHER_U 2
 #define STB_GATHER_UV 3

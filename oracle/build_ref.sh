@@ -8,6 +8,7 @@
 #   oracle/_ref/libstb_ref_slice.so  slice-sampler configuration: PSAMPLE_ARS and
 #                                    LS_NOPOLYGAMMA undefined and polygamma.c added, so that
 #                                    samplea/sampleb run SliceSimple and bmax/digammaInv exist.
+#   oracle/_ref/libstb_ref_slice_m.so  the slice configuration with -DSAMPLEA_M: samplea2 as well.
 #
 # The two switches are "#define"s inside lib/psample.h:37 and lib/digamma.h:25, not -D flags, so the
 # slice build compiles through a throw-away directory under /tmp that holds symlinks to the sources
@@ -42,7 +43,11 @@ sed 's|^#define LS_NOPOLYGAMMA|// &|' "$REF/lib/digamma.h" > "$TMP/digamma.h"
 files=""
 for s in $SRC polygamma; do files="$files $TMP/$s.c"; done
 $CC $CFLAGS -shared -o "$OUT/libstb_ref_slice.so" $files -lm -lpthread
-echo "built $OUT/libstb_ref.so $OUT/libstb_ref_slice.so"
+# the same with -DSAMPLEA_M (lib/psample.h:30): adds samplea2 / logminus (lib/samplea.c:227-341)
+$CC $CFLAGS -DSAMPLEA_M -shared -o "$OUT/libstb_ref_slice_m.so" $files -lm -lpthread
+# recorder for the gcache_value calls of the reference's aterms2 (tests/ref_samplea2_probe.py)
+$CC -O2 -fPIC -shared -o "$OUT/shim_gcache.so" "$HERE/shim_gcache.c"
+echo "built $OUT/libstb_ref.so $OUT/libstb_ref_slice.so $OUT/libstb_ref_slice_m.so"
 
 # --- the reference's own test programs (test/list.c, test/demo.c, test/check.c), UNMODIFIED ---
 #   oracle/_ref/ref_list      list.c linked with the reference library: generates tests/golden/list_*.txt

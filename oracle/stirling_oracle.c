@@ -190,3 +190,55 @@ double orc_UV(const orc_table *t, unsigned n, unsigned m) {
 
 uint64_t orc_cells_S(uint64_t N, uint64_t M) { return (M - 1) * (M - 2) / 2 + (N - M) * (M - 1); }
 uint64_t orc_cells_V(uint64_t N, uint64_t M) { return M * (M - 1) / 2 + (N - M) * (M - 1); }
+
+/* ------------------------------------------------------------------------------------------ */
+/* samplea2's seat-partition sampler, lib/samplea.c:227-341 (SAMPLEA_M builds)                  */
+/* ------------------------------------------------------------------------------------------ */
+/* lib/samplea.c:233-239 */
+double orc_logminus(double x, double y) {
+  if (y >= x) return -HUGE_VAL;
+  if (y - x < -80) return x - exp(y - x);
+  return x + log(1 - exp(y - x));
+}
+
+/*
+ * One node of lib/samplea.c:290-321: n customers at t tables (1 < t < n) inside table tb; writes
+ * the t-1 sizes m[M-1], M = t-1 .. 1.
+ *   exact == 0: the reference's statements in its order -- one uniform (logu[0] = log u),
+ *     rem = ptot + log u (:294), factor (l - a)(N-l+1)/(l-1) (:303), ptot and rem carried over the
+ *     rounds.  Pinned against the reference itself by tests/ref_samplea2_probe.py.
+ *   exact != 0: P(l | N, M+1) = C(N-1,l-1) (1-a)_{l-1} S^{N-l}_M / S^N_{M+1}; logu[M-1] = log of the
+ *     uniform of round M, rem = that, ptot = S(N, M+1) of the current N, factor (l-1-a)(N-l+1)/(l-1).
+ */
+void orc_partition_node(const orc_table *tb, double a, unsigned n, unsigned t, const double *logu, uint16_t *m,
+                        int exact) {
+  int N = (int)n, M;
+  double ptot = orc_S(tb, n, t);
+  double rem = exact ? 0.0 : ptot + logu[0];
+  for (M = (int)t - 1; M >= 1; M--) {
+    int l;
+    double fact = 0.0;
+    if (exact) {
+      ptot = orc_S(tb, N, M + 1);
+      rem = logu[M - 1];
+    }
+    for (l = 1; l <= N - M; l++) {
+      double term;
+      if (l > 1) fact += log(((exact ? l - 1 : l) - a) * (N - l + 1) / (l - 1));
+      term = fact + orc_S(tb, N - l, M) - ptot;
+      if (term >= rem) break;
+      rem = orc_logminus(rem, term);
+    }
+    if (l > N - M) l = N - M;
+    m[M - 1] = (uint16_t)l;
+    N -= l;
+  }
+}
+
+/* log P(l | N, M+1) of the exact mode, for the tests' normalisation and frequency checks */
+double orc_partition_logp(const orc_table *tb, double a, unsigned N, unsigned M, unsigned l) {
+  double fact = 0.0;
+  unsigned j;
+  for (j = 2; j <= l; j++) fact += log(((double)j - 1 - a) * (N - j + 1) / (j - 1));
+  return fact + orc_S(tb, N - l, M) - orc_S(tb, N, M + 1);
+}

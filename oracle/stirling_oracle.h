@@ -42,6 +42,12 @@ double orc_UV(const orc_table *t, unsigned n, unsigned m);
 double orc_asympt(double a, unsigned n, unsigned m);
 double orc_V_asympt(double a, unsigned n, unsigned m);
 
+/* samplea2's partition sampler (lib/samplea.c:227-341): see stirling_oracle.c */
+double orc_logminus(double x, double y);
+void orc_partition_node(const orc_table *tb, double a, unsigned n, unsigned t, const double *logu, uint16_t *m,
+                        int exact);
+double orc_partition_logp(const orc_table *tb, double a, unsigned N, unsigned M, unsigned l);
+
 /* number of stored cells with m>=2, SURVEY.md section 8 */
 uint64_t orc_cells_S(uint64_t N, uint64_t M);
 uint64_t orc_cells_V(uint64_t N, uint64_t M);

@@ -13,6 +13,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_SO = os.path.join(ORACLE_DIR, "liboracle.so")
 REF_SO = os.path.join(ORACLE_DIR, "_ref", "libstb_ref.so")
 REF_SLICE_SO = os.path.join(ORACLE_DIR, "_ref", "libstb_ref_slice.so")
+REF_SLICE_M_SO = os.path.join(ORACLE_DIR, "_ref", "libstb_ref_slice_m.so")
 
 S_STABLE, S_UVTABLE, S_FLOAT, S_ASYMPT = 1, 2, 4, 64
 
@@ -42,6 +43,10 @@ def oracle() -> C.CDLL:
         L.orc_S1.restype, L.orc_S1.argtypes = d, [vp, u]
         L.orc_asympt.restype, L.orc_asympt.argtypes = d, [d, u, u]
         L.orc_V_asympt.restype, L.orc_V_asympt.argtypes = d, [d, u, u]
+        L.orc_logminus.restype, L.orc_logminus.argtypes = d, [d, d]
+        L.orc_partition_node.restype = None
+        L.orc_partition_node.argtypes = [vp, d, u, u, dp, C.POINTER(C.c_uint16), C.c_int]
+        L.orc_partition_logp.restype, L.orc_partition_logp.argtypes = d, [vp, d, u, u, u]
         L.orc_cells_S.restype, L.orc_cells_S.argtypes = C.c_uint64, [C.c_uint64, C.c_uint64]
         L.orc_cells_V.restype, L.orc_cells_V.argtypes = C.c_uint64, [C.c_uint64, C.c_uint64]
         _oracle = L
