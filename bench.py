@@ -299,7 +299,67 @@ def run_extras():
         _extras_variants(out, stb)
     except Exception as exc:
         out["config2_variants"] = {"error": repr(exc)}
+    try:
+        _extras_samplea2(out, stb, cts, bpar)
+    except Exception as exc:
+        out["config4_samplea2"] = {"error": repr(exc)}
     return out
+
+
+def _extras_samplea2(out, stb, cts, bpar):
+    """config 4's statistics through samplea2 (lib/samplea.c:227-341): the
+    seat-partition kernel over all nodes with 1 < t < n, and the whole call"""
+    import math
+
+    import numpy as np
+
+    L = stb.lib()
+    d, u32p = C.c_double, C.POINTER(C.c_uint32)
+    libc = C.CDLL(None)
+    libc.srand48.argtypes = [C.c_long]
+    libc.drand48.restype = d
+    n = np.concatenate(cts.n_rows)
+    t = np.concatenate(cts.t_rows)
+    keep = (t > 1) & (t < n)
+    n, t = n[keep], t[keep]
+    a0 = 0.5
+    maxn, maxt = int(max(r.max() for r in cts.n_rows)) + 1, int(max(r.max() for r in cts.t_rows)) + 1
+    tab = stb.Table(maxn, maxt, maxn, maxt, a0, stb.S_STABLE)
+    n_m = int((t.astype(np.int64) - 1).sum())
+    rng = np.random.default_rng(4)
+    res = {"nodes": int(n.shape[0]), "sizes_sampled": n_m, "customers": int(n.astype(np.int64).sum())}
+    for name, exact in (("reference_arithmetic", False), ("exact", True)):
+        logu = np.log(rng.random(n_m if exact else n.shape[0]))
+        tab.partition_sample(a0, n[:1000], t[:1000], logu[:int((t[:1000].astype(np.int64) - 1).sum())] if exact else logu[:1000],
+                             exact=exact)  # warm-up
+        best = dev = math.inf
+        for _ in range(3):
+            t0 = time.perf_counter()
+            m, off = tab.partition_sample(a0, n, t, logu, exact=exact)
+            best = min(best, time.perf_counter() - t0)
+            dev = min(dev, tab.last_partition_ms)
+        res[name] = {"wall_ms": best * 1e3, "kernel_ms": dev, "nodes_per_s": n.shape[0] / best, "customers_per_s": res["customers"] / best,
+                     "mean_first_size": float(m[off + t.astype(np.int64) - 2].mean())}
+    libc.srand48(12345)
+    t0 = time.perf_counter()
+    a1 = L.samplea2(a0, tab.sp, *cts.args(), None, bpar.ctypes.data_as(C.POINTER(d)), None, 1, 0)
+    res["samplea2_call"] = {"wall_ms": (time.perf_counter() - t0) * 1e3, "a": a1}
+    tab.free()
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libstb_ref_slice_m.so")
+    if os.path.exists(ref_so):  # the reference built with -DSAMPLEA_M, one host core, the same call
+        R = C.CDLL(ref_so)
+        R.S_make.restype = C.c_void_p
+        R.S_make.argtypes = [C.c_uint] * 4 + [d, C.c_uint32]
+        R.samplea2.restype = d
+        R.samplea2.argtypes = [d, C.c_void_p, C.c_int, C.POINTER(C.c_int), u32p, C.POINTER(u32p),
+                               C.POINTER(C.POINTER(C.c_uint16)), C.c_void_p, C.POINTER(d), C.c_void_p, C.c_int, C.c_int]
+        sp = R.S_make(maxn, maxt, maxn, maxt, a0, 1)
+        libc.srand48(12345)
+        t0 = time.perf_counter()
+        ar = R.samplea2(a0, sp, *cts.args(), None, bpar.ctypes.data_as(C.POINTER(d)), None, 1, 0)
+        res["cpu_reference"] = {"wall_ms": (time.perf_counter() - t0) * 1e3, "cores": 1, "a": ar,
+                                "a_draw_identical": bool(ar == a1)}
+    out["config4_samplea2"] = res
 
 
 def _extras_ars(out, stb, cts, Cn, bpar, a0, r0):

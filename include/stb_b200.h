@@ -123,6 +123,8 @@ void stb_release_caches(void);
 
 /* device milliseconds of the most recent fill (CUDA events around the kernel) */
 double stb_last_fill_ms(const stable_t *sp);
+/* device milliseconds of the most recent stb_partition_sample kernel on this table */
+double stb_last_partition_ms(const stable_t *sp);
 /* device address and row pitch (elements) of the S (which_V==0) or V slab; cell (n,m) at [(n-1)*ld+m-1] */
 const void *stb_device_table(const stable_t *sp, int which_V, size_t *ld);
 /* usable CUDA devices; 0 means every S_make will fail (there is no CPU path) */

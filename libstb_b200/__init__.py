@@ -120,6 +120,7 @@ def lib() -> C.CDLL:
     L.stb_sampleb_batch.restype = C.c_int
     L.stb_sampleb_batch.argtypes = [dp, C.c_size_t, C.c_int, d, d, u32p, u32p, dp, u64p, C.c_int, vp]
     L.stb_last_fill_ms.restype, L.stb_last_fill_ms.argtypes = d, [vp]
+    L.stb_last_partition_ms.restype, L.stb_last_partition_ms.argtypes = d, [vp]
     L.stb_device_table.restype, L.stb_device_table.argtypes = vp, [vp, C.c_int, C.POINTER(C.c_size_t)]
     L.stb_device_count.restype, L.stb_device_count.argtypes = C.c_int, []
     L.stb_last_error.restype, L.stb_last_error.argtypes = C.c_char_p, []
@@ -172,6 +173,9 @@ class Table:
     def usedM(self): return self.hdr.usedM
     @property
     def last_fill_ms(self): return self._L.stb_last_fill_ms(self.sp)
+
+    @property
+    def last_partition_ms(self): return self._L.stb_last_partition_ms(self.sp)
 
     @property
     def ld(self):

@@ -610,6 +610,7 @@ int stb_read_rows(stable_t *sp, int which_V, unsigned n0, unsigned nrows, double
 }
 
 double stb_last_fill_ms(const stable_t *sp) { return stb_cuda_last_fill_ms(sp->impl->dev); }
+double stb_last_partition_ms(const stable_t *sp) { return stb_cuda_last_partition_ms(sp->impl->dev); }
 const void *stb_device_table(const stable_t *sp, int which_V, size_t *ld) {
   if (ld) *ld = stb_cuda_table_ld(sp->impl->dev);
   return stb_cuda_table_ptr(sp->impl->dev, which_V ? STB_TAB_V : STB_TAB_S);

@@ -48,6 +48,10 @@ struct stb_dev {
   uint32_t *g_n, *g_m;
   double *g_out;
   size_t g_cap;
+  // staging of the partition sampler, and the device time of its most recent kernel
+  char *p_buf;
+  size_t p_cap;
+  float last_part_ms;
 };
 
 extern "C" int stb_cuda_device_count(void) {
@@ -101,6 +105,7 @@ extern "C" void stb_cuda_table_destroy(stb_dev_t *d) {
   cudaFree(d->g_n);
   cudaFree(d->g_m);
   cudaFree(d->g_out);
+  cudaFree(d->p_buf);
   stb::strip_state_free(&d->strip);
   cudaEventDestroy(d->ev0);
   cudaEventDestroy(d->ev1);
@@ -162,6 +167,7 @@ extern "C" int stb_cuda_table_reserve(stb_dev_t *d, unsigned N, unsigned M, int 
 extern "C" void *stb_cuda_table_ptr(stb_dev_t *d, int which) { return which == STB_TAB_S ? d->S : d->V; }
 
 extern "C" float stb_cuda_last_fill_ms(const stb_dev_t *d) { return d->last_ms; }
+extern "C" float stb_cuda_last_partition_ms(const stb_dev_t *d) { return d->last_part_ms; }
 
 static int fill_mirror(stb_dev_t *d, double a, unsigned N, unsigned M, double *s1_host) {
   size_t need = 4 * ((size_t)M + 2);
@@ -385,9 +391,13 @@ template <typename T>
 __global__ void partition_kernel(const T *__restrict__ tab, const double *__restrict__ s1, size_t ld, double a,
                                  const uint32_t *__restrict__ n, const uint16_t *__restrict__ t,
                                  const double *__restrict__ logu, const uint32_t *__restrict__ off,
-                                 uint16_t *__restrict__ m, size_t count, int exact) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
+                                 const uint32_t *__restrict__ order, uint16_t *__restrict__ m, size_t count,
+                                 int exact) {
+  const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= count) return;
+  // nodes are taken longest first: the 32 walks of a warp have about the same length, and the
+  // longest walks of all (the critical path of the launch) start at once
+  const size_t i = order[slot];
   int N = (int)n[i];
   const int t0 = (int)t[i];
   auto S = [&](int nn, int mm) -> double {  // S_S, lib/stable.c:941-974, inside the table
@@ -396,27 +406,39 @@ __global__ void partition_kernel(const T *__restrict__ tab, const double *__rest
     return (double)tab[(size_t)(nn - 1) * ld + (mm - 1)];
   };
   double ptot = S(N, t0);
-  double rem = exact ? 0.0 : __dadd_rn(ptot, logu[i]);
+  double rem = exact ? logu[off[i] + t0 - 2] : __dadd_rn(ptot, logu[i]);
   const double shift = exact ? 1.0 : 0.0;
   uint16_t *mp = m + off[i];
-  for (int M = t0 - 1; M >= 1; M--) {
-    if (exact) {
-      ptot = S(N, M + 1);
-      rem = logu[off[i] + M - 1];
-    }
-    double fact = 0.0;
-    int l;
-    for (l = 1; l <= N - M; l++) {
-      if (l > 1)
-        fact = __dadd_rn(fact, log(__ddiv_rn(__dmul_rn(__dsub_rn((double)l - shift, a), (double)(N - l + 1)),
-                                             (double)(l - 1))));
-      const double term = __dsub_rn(__dadd_rn(fact, S(N - l, M)), ptot);
-      if (term >= rem) break;
+  // The reference's two nested loops (rounds M, walk l) as ONE loop that advances the walk by a step
+  // per trip and changes round in a short predicated tail: lanes whose walks end at different l do
+  // not wait for each other at every round boundary, only at the end of the node.
+  int M = t0 - 1, l = 1;
+  double fact = 0.0;
+  while (M >= 1) {
+    if (l > 1)
+      fact = __dadd_rn(fact, log(__ddiv_rn(__dmul_rn(__dsub_rn((double)l - shift, a), (double)(N - l + 1)),
+                                           (double)(l - 1))));
+    const double term = __dsub_rn(__dadd_rn(fact, S(N - l, M)), ptot);
+    bool done = term >= rem;
+    if (!done) {
       rem = logminus_dev(rem, term);
+      l++;
+      if (l > N - M) {  // walked off the end: the last admissible size
+        l = N - M;
+        done = true;
+      }
     }
-    if (l > N - M) l = N - M;
-    mp[M - 1] = (uint16_t)l;
-    N -= l;
+    if (done) {
+      mp[M - 1] = (uint16_t)l;
+      N -= l;
+      M--;
+      l = 1;
+      fact = 0.0;
+      if (exact && M >= 1) {
+        ptot = S(N, M + 1);
+        rem = logu[off[i] + M - 1];
+      }
+    }
   }
 }
 
@@ -428,17 +450,37 @@ extern "C" int stb_cuda_partition(stb_dev_t *d, double a, const uint32_t *n, con
     return -1;
   }
   if (count == 0 || n_m == 0) return 0;
-  // one staging block: n, off (u32), logu (f64), t (u16), m (u16)
+  // the nodes by decreasing n (counting sort; n <= capN was checked by the caller)
+  std::vector<uint32_t> order(count), start((size_t)d->capN + 2, 0);
+  for (size_t i = 0; i < count; i++) {
+    if (n[i] > d->capN) {
+      snprintf(g_err, sizeof g_err, "stb_cuda_partition: n beyond the table");
+      return -1;
+    }
+    start[d->capN - n[i] + 1]++;
+  }
+  for (size_t v = 1; v < start.size(); v++) start[v] += start[v - 1];
+  for (size_t i = 0; i < count; i++) order[start[d->capN - n[i]]++] = (uint32_t)i;
+  // one staging block: logu (f64), n, off, order (u32), t (u16), m (u16)
   const size_t b_n = count * sizeof(uint32_t), b_u = (exact ? n_m : count) * sizeof(double), b_t = count * sizeof(uint16_t),
                b_m = n_m * sizeof(uint16_t);
-  const size_t o_u = 0, o_n = o_u + b_u, o_off = o_n + b_n, o_t = o_off + b_n, o_m = (o_t + b_t + 7) & ~(size_t)7;
-  char *buf = NULL;
-  CK(cudaMalloc(&buf, o_m + b_m));
+  const size_t o_u = 0, o_n = o_u + b_u, o_off = o_n + b_n, o_ord = o_off + b_n, o_t = o_ord + b_n,
+               o_m = (o_t + b_t + 7) & ~(size_t)7;
+  if (o_m + b_m > d->p_cap) {
+    cudaFree(d->p_buf);
+    d->p_buf = NULL;
+    d->p_cap = 0;
+    CK(cudaMalloc(&d->p_buf, o_m + b_m));
+    d->p_cap = o_m + b_m;
+  }
+  char *buf = d->p_buf;
   cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(buf + o_ord, order.data(), b_n, cudaMemcpyHostToDevice, d->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(buf + o_u, logu, b_u, cudaMemcpyHostToDevice, d->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(buf + o_n, n, b_n, cudaMemcpyHostToDevice, d->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(buf + o_off, off, b_n, cudaMemcpyHostToDevice, d->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(buf + o_t, t, b_t, cudaMemcpyHostToDevice, d->stream);
+  if (e == cudaSuccess) e = cudaEventRecord(d->ev0, d->stream);
   if (e == cudaSuccess) {
     // 64 threads per block: nodes differ in length by orders of magnitude, small blocks spread the long ones
     const unsigned blocks = (unsigned)((count + 63) / 64);
@@ -446,17 +488,20 @@ extern "C" int stb_cuda_partition(stb_dev_t *d, double a, const uint32_t *n, con
       partition_kernel<float><<<blocks, 64, 0, d->stream>>>((const float *)d->S, d->s1, d->ld, a,
                                                             (const uint32_t *)(buf + o_n), (const uint16_t *)(buf + o_t),
                                                             (const double *)(buf + o_u), (const uint32_t *)(buf + o_off),
-                                                            (uint16_t *)(buf + o_m), count, exact);
+                                                            (const uint32_t *)(buf + o_ord), (uint16_t *)(buf + o_m), count,
+                                                            exact);
     else
       partition_kernel<double><<<blocks, 64, 0, d->stream>>>((const double *)d->S, d->s1, d->ld, a,
                                                              (const uint32_t *)(buf + o_n), (const uint16_t *)(buf + o_t),
                                                              (const double *)(buf + o_u), (const uint32_t *)(buf + o_off),
-                                                             (uint16_t *)(buf + o_m), count, exact);
+                                                             (const uint32_t *)(buf + o_ord), (uint16_t *)(buf + o_m), count,
+                                                             exact);
     e = cudaGetLastError();
   }
+  if (e == cudaSuccess) e = cudaEventRecord(d->ev1, d->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(m_out, buf + o_m, b_m, cudaMemcpyDeviceToHost, d->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
-  cudaFree(buf);
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&d->last_part_ms, d->ev0, d->ev1);
   if (e != cudaSuccess) return fail(e, "stb_cuda_partition");
   return 0;
 }

@@ -63,6 +63,8 @@ int stb_cuda_fill(stb_dev_t *d, double a, unsigned startN, unsigned startM, unsi
 int stb_cuda_read_s1(stb_dev_t *d, unsigned N, double *dst);
 /* milliseconds the device spent in the most recent stb_cuda_fill (CUDA events) */
 float stb_cuda_last_fill_ms(const stb_dev_t *d);
+/* milliseconds the device spent in the most recent stb_cuda_partition kernel */
+float stb_cuda_last_partition_ms(const stb_dev_t *d);
 
 /*
  * Copy rows [row0, row0+nrows) (0-based row index = n-1) of one table to host memory as
