@@ -414,11 +414,16 @@ __global__ void partition_kernel(const T *__restrict__ tab, const double *__rest
   // not wait for each other at every round boundary, only at the end of the node.
   int M = t0 - 1, l = 1;
   double fact = 0.0;
+  // the table cell of the NEXT step is fetched a step ahead: its address does not depend on the
+  // remainder, its L2 latency (the longest link of a step) then overlaps the exp/log chain
+  double s_next = S(N - 1, M);
   while (M >= 1) {
+    const double s_cur = s_next;
+    s_next = S(N - (l + 1 <= N - M ? l + 1 : l), M);
     if (l > 1)
       fact = __dadd_rn(fact, log(__ddiv_rn(__dmul_rn(__dsub_rn((double)l - shift, a), (double)(N - l + 1)),
                                            (double)(l - 1))));
-    const double term = __dsub_rn(__dadd_rn(fact, S(N - l, M)), ptot);
+    const double term = __dsub_rn(__dadd_rn(fact, s_cur), ptot);
     bool done = term >= rem;
     if (!done) {
       rem = logminus_dev(rem, term);
@@ -434,9 +439,12 @@ __global__ void partition_kernel(const T *__restrict__ tab, const double *__rest
       M--;
       l = 1;
       fact = 0.0;
-      if (exact && M >= 1) {
-        ptot = S(N, M + 1);
-        rem = logu[off[i] + M - 1];
+      if (M >= 1) {
+        s_next = S(N - 1, M);
+        if (exact) {
+          ptot = S(N, M + 1);
+          rem = logu[off[i] + M - 1];
+        }
       }
     }
   }
