@@ -306,6 +306,12 @@ __device__ __forceinline__ void strip_steps(double (&x)[K], const double (&ma)[K
         sts_f64(xr + ((i - 1) * CP + k) * 8, x[k]);
         if (DUP) sts_f64(xr + ((RS + i - 1) * CP + k) * 8, x[k]);
       }
+      // the neighbour's value of the previous row (for V), deferred the same way: stored in its own
+      // step it waited for the load and the multiply that made it
+      if (HAS_V) {
+        sts_f64(yr + (i - 1) * 32 * 8, yin);
+        if (DUP) sts_f64(yr + (RS + i - 1) * 32 * 8, yin);
+      }
     }
 #pragma unroll
     for (int k = K - 1; k >= 1; k--) x[k] = fma(nm1 - ma[k], x[k], x[k - 1]);
@@ -315,12 +321,12 @@ __device__ __forceinline__ void strip_steps(double (&x)[K], const double (&ma)[K
     if (DUP) sts_f64(xr + ((RS + i) * CP + K - 1) * 8, x[K - 1]);
     sts_f64_if(outp + i * 8, x[K - 1], write_out);
     yin = nb * ((FIRST && i == 0) ? scn0 : scn);
-    if (HAS_V) {
-      sts_f64(yr + i * 32 * 8, yin);
-      if (DUP) sts_f64(yr + (RS + i) * 32 * 8, yin);
-    }
   }
   // the last row's remaining columns
+  if (HAS_V) {
+    sts_f64(yr + (ST_RB - 1) * 32 * 8, yin);
+    if (DUP) sts_f64(yr + (RS + ST_RB - 1) * 32 * 8, yin);
+  }
 #pragma unroll
   for (int k = 0; k < K - 1; k++) {
     sts_f64(xr + ((ST_RB - 1) * CP + k) * 8, x[k]);
