@@ -282,7 +282,8 @@ extern "C" int stb_cuda_read_rows(stb_dev_t *d, int which, unsigned row0, unsign
  * lib/stable.c:875-883), STB_GATHER_UV = (n - m a) V + 1 (m == 1: -inf, m == n+1: 1, m == n: (n+1)/(n-1),
  * lib/stable.c:885-897); m == 0 answers NaN for U (the scalar call exits) */
 template <typename T>
-__global__ void gather_kernel(const T *__restrict__ tab, size_t ld, int what, double a, unsigned usedN, unsigned usedM,
+__global__ void gather_kernel(const T *__restrict__ tab, const double *__restrict__ s1, size_t ld, int what, double a,
+                              unsigned usedN, unsigned usedM,
                               const uint32_t *__restrict__ n, const uint32_t *__restrict__ m,
                               double *__restrict__ out, size_t count) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -294,6 +295,8 @@ __global__ void gather_kernel(const T *__restrict__ tab, size_t ld, int what, do
       v = 0.0;
     else if (mm == 0 || nn < mm || nn > usedN || mm > usedM)
       v = -HUGE_VAL;
+    else if (mm == 1)
+      v = s1[nn - 1];  // S_S(n,1) is S_S1(n): FP64 also when the table stores floats (lib/stable.c:946-947)
     else
       v = (double)tab[(size_t)(nn - 1) * ld + (mm - 1)];
   } else {
@@ -347,11 +350,11 @@ extern "C" int stb_cuda_gather(stb_dev_t *d, int which, double a, unsigned usedN
   }
   unsigned blocks = (unsigned)((count + 255) / 256);
   if (d->is_float)
-    gather_kernel<float><<<blocks, 256, 0, d->stream>>>((const float *)tab, d->ld, which, a, usedN, usedM, dn, dm, dout,
-                                                        count);
+    gather_kernel<float><<<blocks, 256, 0, d->stream>>>((const float *)tab, d->s1, d->ld, which, a, usedN, usedM, dn, dm,
+                                                        dout, count);
   else
-    gather_kernel<double><<<blocks, 256, 0, d->stream>>>((const double *)tab, d->ld, which, a, usedN, usedM, dn, dm,
-                                                         dout, count);
+    gather_kernel<double><<<blocks, 256, 0, d->stream>>>((const double *)tab, d->s1, d->ld, which, a, usedN, usedM, dn,
+                                                         dm, dout, count);
   CK(cudaGetLastError());
   if (!on_device)
     CK(cudaMemcpyAsync(out, d->g_out, count * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
@@ -540,7 +543,8 @@ struct stb_sweep_dev {
 
 /* S_S conventions (lib/stable.c:941-949) on a dense slab; partial sums per block in a fixed order */
 template <typename T>
-__global__ void sweep_gather_kernel(const T *__restrict__ slabs, size_t slab_elems, size_t ld, unsigned N, unsigned M,
+__global__ void sweep_gather_kernel(const T *__restrict__ slabs, const double *__restrict__ s1s, size_t slab_elems,
+                                    size_t ld, unsigned N, unsigned M,
                                     const uint32_t *__restrict__ n, const uint32_t *__restrict__ m, size_t npairs,
                                     double *__restrict__ gather, double *__restrict__ partial) {
   __shared__ double red[256];
@@ -554,6 +558,8 @@ __global__ void sweep_gather_kernel(const T *__restrict__ slabs, size_t slab_ele
       v = 0.0;
     else if (mm == 0 || nn < mm || nn > N || mm > M)
       v = -HUGE_VAL;
+    else if (mm == 1)
+      v = s1s[(size_t)tb * N + (nn - 1)];  // S_S(n,1) = S_S1(n), FP64 whatever the table stores
     else
       v = (double)tab[(size_t)(nn - 1) * ld + (mm - 1)];
     if (gather) gather[(size_t)tb * npairs + i] = v;
@@ -737,11 +743,11 @@ extern "C" int stb_cuda_sweep_run(stb_sweep_dev_t *w, const double *a, size_t na
     if (gather_out || sum_out) {
       dim3 grid((unsigned)nblk, (unsigned)nt);
       if (w->is_float)
-        sweep_gather_kernel<float><<<grid, 256, 0, w->stream>>>((const float *)w->slab, slab_elems, w->ld, w->N, w->M,
+        sweep_gather_kernel<float><<<grid, 256, 0, w->stream>>>((const float *)w->slab, w->s1, slab_elems, w->ld, w->N, w->M,
                                                                   w->d_n, w->d_m, w->npairs,
                                                                   gather_out ? w->d_gather : NULL, w->d_partial);
       else
-        sweep_gather_kernel<double><<<grid, 256, 0, w->stream>>>((const double *)w->slab, slab_elems, w->ld, w->N,
+        sweep_gather_kernel<double><<<grid, 256, 0, w->stream>>>((const double *)w->slab, w->s1, slab_elems, w->ld, w->N,
                                                                    w->M, w->d_n, w->d_m, w->npairs,
                                                                    gather_out ? w->d_gather : NULL, w->d_partial);
       CK(cudaGetLastError());

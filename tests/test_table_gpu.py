@@ -75,6 +75,26 @@ def test_float_storage(flags):
     t.free()
 
 
+def test_float_table_answers_the_first_column_in_fp64():
+    """S_S(n,1) is S_S1(n) (lib/stable.c:946-947): FP64 also for S_FLOAT tables -- scalar call, batched
+    gather and sweep gather alike."""
+    N, M, a = 900, 60, 0.45
+    t = stb.Table(N, M, N, M, a, stb.S_STABLE | stb.S_FLOAT)
+    S, _ = harness.oracle_tables(N, M, a, want_V=False)
+    n = np.arange(2, N + 1, dtype=np.uint32)
+    one = np.ones_like(n)
+    got = t.S_batch(n, one)
+    assert harness.close(got, S[n - 1, 0]).all()
+    assert not np.array_equal(got, got.astype(np.float32).astype(np.float64)), "not float-rounded"
+    assert all(t.S(int(v), 1) == g for v, g in zip(n[::97], got[::97]))
+    t.free()
+    w = stb.Sweep(N, M, stb.S_STABLE | stb.S_FLOAT)
+    w.set_pairs(n, one)
+    g, _, _ = w.run(np.array([a]), gather=True, sums=False)
+    w.free()
+    assert harness.close(g[0], S[n - 1, 0]).all()
+
+
 @pytest.mark.parametrize("flags", [stb.S_STABLE, stb.S_UVTABLE])
 def test_single_table_flags(flags):
     N, M, a = 900, 100, 0.35
