@@ -171,10 +171,21 @@ static double bmax(double x, BLData *mp) { /* lib/sampleb.c:51-68: a few fixed-p
   return x_prime;
 }
 
-static int g_sampler = STB_SAMPLER_SLICE;
+/* which sampler samplea / sampleb / samplea2 run: a compile-time switch in the reference
+ * (PSAMPLE_ARS, lib/psample.h:37), a run-time one here.  Unmodified callers pick the reference's
+ * default build with STB_SAMPLER=ars in the environment (read once, at the first use). */
+static int g_sampler_state = -1;
+static int sampler_mode(void) {
+  if (g_sampler_state < 0) {
+    const char *s = getenv("STB_SAMPLER");
+    g_sampler_state = (s && (!strcmp(s, "ars") || !strcmp(s, "ARS") || !strcmp(s, "1"))) ? STB_SAMPLER_ARS : STB_SAMPLER_SLICE;
+  }
+  return g_sampler_state;
+}
+#define g_sampler (sampler_mode())
 int stb_set_sampler(int which) {
-  const int old = g_sampler;
-  g_sampler = which == STB_SAMPLER_ARS ? STB_SAMPLER_ARS : STB_SAMPLER_SLICE;
+  const int old = sampler_mode();
+  g_sampler_state = which == STB_SAMPLER_ARS ? STB_SAMPLER_ARS : STB_SAMPLER_SLICE;
   return old;
 }
 

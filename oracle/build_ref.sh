@@ -55,6 +55,13 @@ echo "built $OUT/libstb_ref.so $OUT/libstb_ref_slice.so $OUT/libstb_ref_slice_m.
 #                             the same sources compiled against THIS repo's include/ and linked with
 #                             libstb_b200.so: the drop-in proof (they need a GPU to run)
 $CC -O2 -w -I"$REF/lib" "$REF/test/list.c" -o "$OUT/ref_list" "$OUT/libstb_ref.so" -Wl,-rpath,'$ORIGIN' -lm
+#   oracle/_ref/ref_demo, ref_check   demo.c / check.c linked with the reference library (its default, ARS,
+#                             configuration), and shim_time.so, the fixed clock that makes them (and the
+#                             drop-in builds below) deterministic: tests/golden/programs/*.txt
+for p in demo check; do
+  $CC -O2 -w -I"$REF/lib" "$REF/test/$p.c" -o "$OUT/ref_$p" "$OUT/libstb_ref.so" -Wl,-rpath,'$ORIGIN' -lm
+done
+$CC -O2 -fPIC -shared -o "$OUT/shim_time.so" "$HERE/shim_time.c"
 LIBDIR="$HERE/../libstb_b200/lib"
 if [ -f "$LIBDIR/libstb_b200.so" ]; then
   for p in list demo check; do

@@ -15,6 +15,8 @@ import pytest
 
 from tests import harness
 from tests.golden.make_golden_list import CASES
+from tests.golden.make_golden_programs import CASES as PROGRAM_CASES
+from tests.golden.make_golden_programs import run as run_fixed_clock
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DROPIN = {p: os.path.join(ROOT, "oracle", "_ref", "dropin_" + p) for p in ("list", "demo", "check")}
@@ -94,3 +96,31 @@ def test_demo_and_check_programs_run_end_to_end():
     b = float(re.search(r"Run ave b: = ([0-9.]+)", out).group(1))
     T = float(re.search(r"Run ave T: = ([0-9.]+)", out).group(1))
     assert 0.01 <= a <= 0.98 and 0.01 <= b <= 2000 and 5 <= T <= 200
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", sorted(PROGRAM_CASES))
+def test_demo_and_check_output_matches_reference_under_a_fixed_clock(case):
+    """The reference's simulation programs -- Gibbs sweeps over table counts through S_V / S_S / S_U,
+    samplea / sampleb (ARS, the reference's default build) or the programs' own slice / ARS code every
+    few cycles, S_remake after every new discount -- print what they print when linked with the
+    reference library: same source, same seeds, same clock (oracle/_ref/shim_time.so; goldens from
+    tests/golden/make_golden_programs.py).  Every accept/reject of thousands of draws has to agree
+    for the summaries to agree; numbers are compared at 2e-6 relative (6 digits are printed)."""
+    prog, args = PROGRAM_CASES[case]
+    shim = os.path.join(ROOT, "oracle", "_ref", "shim_time.so")
+    if not (os.path.exists(DROPIN[prog]) and os.path.exists(shim)):
+        pytest.skip("oracle/_ref/dropin_* not built")
+    want = open(os.path.join(ROOT, "tests", "golden", "programs", case + ".txt")).read().splitlines()
+    got = run_fixed_clock(DROPIN[prog], args, {"STB_SAMPLER": "ars"})
+    assert got.returncode == 0, got.stdout[-2000:]
+    keep = lambda lines: [l for l in lines if l.strip() and not l.startswith(("S-table", "Time"))]
+    w, g = keep(want), keep(got.stdout.splitlines())
+    assert len(w) == len(g), (w, g)
+    bad = []
+    for lw, lg in zip(w, g):
+        nw, ng = NUM.findall(lw), NUM.findall(lg)
+        if NUM.sub("#", lw) != NUM.sub("#", lg) or len(nw) != len(ng) or not all(
+                _numbers_match(a, b) for a, b in zip(nw, ng)):
+            bad.append((lw, lg))
+    assert not bad, bad[:6]
