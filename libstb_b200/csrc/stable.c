@@ -509,7 +509,15 @@ static int batch(stable_t *sp, int which, const uint32_t *n, const uint32_t *m, 
     if (maxn > sp->usedN || maxm > sp->usedM)
       if (extend(sp, maxn > sp->usedN ? maxn : sp->usedN, maxm > sp->usedM ? maxm : sp->usedM)) return 1;
   }
-  return stb_cuda_gather(sp->impl->dev, which, sp->a, sp->usedN, sp->usedM, n, m, out, count, on_device);
+  {
+    /* exclusive: the call uses the handle's stream and staging buffers, and a growth in another
+     * thread (S_THREADS) would move the table under the kernel */
+    int rc;
+    lock(sp);
+    rc = stb_cuda_gather(sp->impl->dev, which, sp->a, sp->usedN, sp->usedM, n, m, out, count, on_device);
+    unlock(sp);
+    return rc;
+  }
 }
 
 int stb_S_batch(stable_t *sp, const uint32_t *n, const uint32_t *m, double *out, size_t count) {
@@ -561,7 +569,13 @@ int stb_partition_sample(stable_t *sp, double a, const uint32_t *n, const uint16
   }
   if (maxn > sp->usedN || maxt > sp->usedM)
     if (extend(sp, maxn > sp->usedN ? maxn : sp->usedN, maxt > sp->usedM ? maxt : sp->usedM)) return 1;
-  return stb_cuda_partition(sp->impl->dev, a, n, t, logu, off, count, m_out, n_m, exact);
+  {
+    int rc;
+    lock(sp); /* exclusive, like the batched look-ups */
+    rc = stb_cuda_partition(sp->impl->dev, a, n, t, logu, off, count, m_out, n_m, exact);
+    unlock(sp);
+    return rc;
+  }
 }
 
 /* ------------------------------------------------------------------------------------------ */

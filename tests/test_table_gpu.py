@@ -332,6 +332,11 @@ def test_concurrent_lookups_with_growth_S_THREADS():
             top = min(Nmax - 2, int(top * 1.02) + 5)  # reach further and further: growth on the way
             n = int(rng.integers(3, top))
             m = int(rng.integers(2, min(n, Mmax - 2)))
+            if seed % 2 and it % 8 == 0:  # batched look-ups (one kernel on the handle's stream) in between
+                nn = rng.integers(3, top, size=64).astype(np.uint32)
+                mm = np.minimum(rng.integers(2, Mmax - 2, size=64), nn - 1).astype(np.uint32)
+                if not harness.close(t.S_batch(nn, mm), S[nn - 1, mm - 1]).all():
+                    errs.append(("batch", int(nn[0]), int(mm[0])))
             s, v = t.S(n, m), t.V(n, m)
             if not (abs(s - S[n - 1, m - 1]) <= 1e-12 * max(1.0, abs(S[n - 1, m - 1])) and
                     abs(v - V[n - 1, m - 1]) <= 1e-12 * max(1.0, abs(V[n - 1, m - 1]))):
