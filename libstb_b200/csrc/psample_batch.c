@@ -87,17 +87,32 @@ static void trace_add(stb_sample_stats *st, size_t c, double x, double v) {
   st->trace_n[c]++;
 }
 
-/* xp[c]: start and result; lo[c], hi[c]: bounds.  Returns 0, or 1 + index of the first failing chain */
+/*
+ * xp[c]: start and result; lo[c], hi[c]: bounds.  Returns 0, or 1 + index of the first failing chain.
+ *
+ * depth > 1: speculative proposals.  A slice sampler's proposals do not depend on the density: the
+ * next one is drawn uniformly from the bracket, and a rejected proposal shrinks the bracket towards
+ * the current point -- the density only decides where the sequence STOPS.  So a round may evaluate
+ * the next `depth` proposals of every chain at once (made from a COPY of the chain's stream) and
+ * then replay the sampler over the values: the first accepted proposal ends the replay, the stream
+ * advances by exactly the uniforms the sequential sampler would have drawn, and the proposals behind
+ * an acceptance are dropped.  Same draws, same stream, fewer device round trips; worth it when an
+ * evaluation is cheap (sampleb: a 1000-term reduction) and not when it is a table fill (samplea: 1).
+ */
 static int slice_lockstep(double *xp, size_t C, const double *lo, const double *hi, uint64_t *rng, int loops,
-                          eval_fn eval, void *ctx, stb_sample_stats *st) {
+                          eval_fn eval, void *ctx, stb_sample_stats *st, int depth) {
+  const size_t W = (size_t)(depth < 1 ? 1 : depth) + 1; /* evaluations per chain and round, at most */
   int *phase = (int *)malloc(sizeof(int) * C), *left = (int *)malloc(sizeof(int) * C);
-  int *tries = (int *)malloc(sizeof(int) * C), *chain = (int *)malloc(sizeof(int) * C);
+  int *tries = (int *)malloc(sizeof(int) * C), *chain = (int *)malloc(sizeof(int) * C * W);
+  int *nprop = (int *)malloc(sizeof(int) * C);
+  size_t *first = (size_t *)malloc(sizeof(size_t) * C);
   double *y = (double *)malloc(sizeof(double) * C), *r0 = (double *)malloc(sizeof(double) * C);
-  double *r1 = (double *)malloc(sizeof(double) * C), *xq = (double *)malloc(sizeof(double) * C);
-  double *val = (double *)malloc(sizeof(double) * C);
+  double *r1 = (double *)malloc(sizeof(double) * C), *xq = (double *)malloc(sizeof(double) * C * W);
+  double *val = (double *)malloc(sizeof(double) * C * W);
   size_t c, cnt;
   int rc = 0;
-  if (!phase || !left || !tries || !chain || !y || !r0 || !r1 || !xq || !val) {
+  if (depth < 1) depth = 1;
+  if (!phase || !left || !tries || !chain || !nprop || !first || !y || !r0 || !r1 || !xq || !val) {
     rc = -1;
     goto done;
   }
@@ -116,15 +131,36 @@ static int slice_lockstep(double *xp, size_t C, const double *lo, const double *
     cnt = 0;
     for (c = 0; c < C; c++) {
       stb_rng48 r;
+      double b0, b1;
+      int np, k, tr;
       if (phase[c] == PH_DONE) continue;
-      if (phase[c] == PH_NEED_Y)
+      first[c] = cnt;
+      r.x = rng[c]; /* a copy: the stream itself advances in the replay below */
+      if (phase[c] == PH_NEED_Y) {
         xq[cnt] = xp[c];
-      else {
-        r.x = rng[c];
-        xq[cnt] = r0[c] + stb_rng48_unit(&r) * (r1[c] - r0[c]);
-        rng[c] = r.x;
+        chain[cnt++] = (int)c;
+        (void)stb_rng48_unit(&r); /* the uniform of the slice level comes first */
+        b0 = lo[c];
+        b1 = hi[c];
+        tr = 1;
+        np = depth - 1;
+      } else {
+        b0 = r0[c];
+        b1 = r1[c];
+        tr = tries[c];
+        np = depth;
       }
-      chain[cnt++] = (int)c;
+      if (np > TOOMANY - tr) np = TOOMANY - tr; /* the sequential sampler gives up there */
+      for (k = 0; k < np; k++) {
+        const double x = b0 + stb_rng48_unit(&r) * (b1 - b0);
+        xq[cnt] = x;
+        chain[cnt++] = (int)c;
+        if (x < xp[c])
+          b0 = x;
+        else
+          b1 = x;
+      }
+      nprop[c] = np;
     }
     if (!cnt) break;
     if (eval(ctx, xq, chain, cnt, val)) {
@@ -135,36 +171,45 @@ static int slice_lockstep(double *xp, size_t C, const double *lo, const double *
       st->evals += cnt;
       st->rounds++;
     }
-    for (size_t j = 0; j < cnt; j++) {
+    /* replay the sequential sampler over the values */
+    for (c = 0; c < C; c++) {
       stb_rng48 r;
-      c = (size_t)chain[j];
-      trace_add(st, c, xq[j], val[j]);
+      size_t j;
+      int k;
+      if (phase[c] == PH_DONE) continue;
+      j = first[c];
+      r.x = rng[c];
       if (phase[c] == PH_NEED_Y) {
-        r.x = rng[c];
+        trace_add(st, c, xq[j], val[j]);
         y[c] = val[j] + log(stb_rng48_unit(&r));
-        rng[c] = r.x;
         r0[c] = lo[c];
         r1[c] = hi[c];
         tries[c] = 1;
         phase[c] = PH_TRY;
-      } else {
+        j++;
+      }
+      for (k = 0; k < nprop[c]; k++, j++) {
+        const double x = r0[c] + stb_rng48_unit(&r) * (r1[c] - r0[c]); /* == xq[j], bit for bit */
+        trace_add(st, c, x, val[j]);
         if (val[j] > y[c]) {
-          xp[c] = xq[j];
+          xp[c] = x;
           left[c]--;
           phase[c] = left[c] > 0 ? PH_NEED_Y : PH_DONE;
-        } else {
-          if (xq[j] < xp[c])
-            r0[c] = xq[j];
-          else
-            r1[c] = xq[j];
-          if (++tries[c] >= TOOMANY) {
-            fprintf(stderr, "SliceSimple: giving up after %d tries, range=[%lg,%lg] (chain %zu)\n", TOOMANY, r0[c],
-                    r1[c], c);
-            rc = 1 + (int)c;
-            goto done;
-          }
+          break;
+        }
+        if (x < xp[c])
+          r0[c] = x;
+        else
+          r1[c] = x;
+        if (++tries[c] >= TOOMANY) {
+          fprintf(stderr, "SliceSimple: giving up after %d tries, range=[%lg,%lg] (chain %zu)\n", TOOMANY, r0[c],
+                  r1[c], c);
+          rc = 1 + (int)c;
+          rng[c] = r.x;
+          goto done;
         }
       }
+      rng[c] = r.x;
     }
   }
 done:
@@ -172,6 +217,8 @@ done:
   free(left);
   free(tries);
   free(chain);
+  free(nprop);
+  free(first);
   free(y);
   free(r0);
   free(r1);
@@ -403,7 +450,7 @@ static int samplea_batch_core(double *a, size_t C, int I, const int *K, const sc
         rc = 1 + (int)c;
       }
   } else
-    rc = slice_lockstep(a, C, lo, hi, rng, loops, aterms_batch, &ab, st);
+    rc = slice_lockstep(a, C, lo, hi, rng, loops, aterms_batch, &ab, st, 1);
 done:
   if (ab.sweep) sweep_release(ab.sweep, Nx, Mx);
   if (ab.ps) stb_cuda_pstat_destroy(ab.ps);
@@ -453,6 +500,7 @@ static int bterms_batch(void *ctx, const double *x, const int *chain, size_t cnt
 
 #define B_ERROR 1.0e-4
 #define B_LOOPS 5
+#define B_SPECULATE 4 /* slice proposals evaluated per chain and round (see slice_lockstep) */
 
 static int sampleb_batch_core(double *b, size_t C, int I, double shape, double scale, const scnt_int *N,
                               const scnt_int *T, const double *apar, uint64_t *rng, stb_rand31_t *rnd, int loops,
@@ -480,10 +528,10 @@ static int sampleb_batch_core(double *b, size_t C, int I, double shape, double s
   as = (double *)malloc(sizeof(double) * C);
   idx = (int *)malloc(sizeof(int) * C);
   bl = (int *)malloc(sizeof(int) * C);
-  bb.qv = (double *)malloc(sizeof(double) * C);
-  bb.av = (double *)malloc(sizeof(double) * C);
+  bb.qv = (double *)malloc(sizeof(double) * C * (B_SPECULATE + 1));
+  bb.av = (double *)malloc(sizeof(double) * C * (B_SPECULATE + 1));
   if (!Q || !lo || !hi || !x || !xprime || !dsum || !xs || !as || !idx || !bl || !bb.qv || !bb.av) goto done;
-  bb.ps = stb_cuda_pstat_create(I, T, N, NULL, 0, C);
+  bb.ps = stb_cuda_pstat_create(I, T, N, NULL, 0, C * (B_SPECULATE + 1));
   if (!bb.ps) goto done;
   /* auxiliary variables: Q_c = 1/scale - sum_i log q_i, q_i ~ Beta(b_c, N_i)  (lib/sampleb.c:90-100) */
   if (stb_cuda_pstat_betaQ(bb.ps, b, rng, C, scale, Q, &ms)) goto done;
@@ -601,7 +649,7 @@ static int sampleb_batch_core(double *b, size_t C, int I, double shape, double s
         free(g2);
       }
     } else
-      rc = slice_lockstep(xs, cnt, lo, hi, r2, loops, bterms_batch, &bb, sp);
+      rc = slice_lockstep(xs, cnt, lo, hi, r2, loops, bterms_batch, &bb, sp, B_SPECULATE);
     if (st) {
       st->evals = sub.evals;
       st->rounds = sub.rounds;
