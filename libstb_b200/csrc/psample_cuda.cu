@@ -107,8 +107,10 @@ __global__ void k_bdigamma(const uint32_t *__restrict__ T, int I, const double *
 __global__ void k_betaQ(const uint32_t *__restrict__ N, int I, const double *__restrict__ b_in,
                         unsigned long long *__restrict__ rng, double scale, const stb_zig_tables *__restrict__ zt,
                         double *__restrict__ Q, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  // ONE chain per warp, on lane 0: the draws are rejection loops of data-dependent length, and 32
+  // chains in one warp would each pay for the longest of them at every step
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= C || (threadIdx.x & 31)) return;
   stb_rng48 r;
   r.x = rng[c];
   double q = 1.0 / scale;
@@ -248,7 +250,7 @@ extern "C" int stb_cuda_pstat_betaQ(stb_pstat_dev_t *p, const double *b_in, uint
   if (stage_in(p, p->dx, b_in, C)) return -1;
   PCK(cudaMemcpyAsync(p->drng, rng, C * sizeof(uint64_t), cudaMemcpyHostToDevice, p->stream));
   PCK(cudaEventRecord(p->ev0, p->stream));
-  k_betaQ<<<(unsigned)((C + 63) / 64), 64, 0, p->stream>>>(p->dN, p->I, p->dx, p->drng, scale, p->dzig, p->dout, (int)C);
+  k_betaQ<<<(unsigned)((C + 1) / 2), 64, 0, p->stream>>>(p->dN, p->I, p->dx, p->drng, scale, p->dzig, p->dout, (int)C);
   PCK(cudaGetLastError());
   PCK(cudaEventRecord(p->ev1, p->stream));
   PCK(cudaMemcpyAsync(Q, p->dout, C * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
