@@ -100,7 +100,7 @@ double stb_rng48_gamma(uint64_t *state, double a);
 double stb_rng48_beta(uint64_t *state, double a, double b);
 
 typedef struct stb_sample_stats {
-  uint64_t evals;  /* log-posterior evaluations over all chains */
+  uint64_t evals;  /* log-posterior evaluations over all chains (speculative slice proposals included) */
   uint64_t rounds; /* lock-step rounds (batched evaluations) */
   double eval_ms;  /* device milliseconds spent in the evaluations */
   /* optional trace: chain c's evaluated points / values in order at [c*trace_cap + k], count in trace_n[c] */

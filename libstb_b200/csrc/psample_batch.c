@@ -97,10 +97,13 @@ static void trace_add(stb_sample_stats *st, size_t c, double x, double v) {
  * then replay the sampler over the values: the first accepted proposal ends the replay, the stream
  * advances by exactly the uniforms the sequential sampler would have drawn, and the proposals behind
  * an acceptance are dropped.  Same draws, same stream, fewer device round trips; worth it when an
- * evaluation is cheap (sampleb: a 1000-term reduction) and not when it is a table fill (samplea: 1).
+ * evaluation is cheap (sampleb: a 1000-term reduction).  When it is a table fill (samplea), the device
+ * works in waves of `slots` evaluations that cost the same full or not: slots > 0 hands only the
+ * slots a round would leave empty in its last wave to speculative proposals (they cost nothing), so
+ * the long tail of rounds with a few chains left collapses.
  */
 static int slice_lockstep(double *xp, size_t C, const double *lo, const double *hi, uint64_t *rng, int loops,
-                          eval_fn eval, void *ctx, stb_sample_stats *st, int depth) {
+                          eval_fn eval, void *ctx, stb_sample_stats *st, int depth, size_t slots) {
   const size_t W = (size_t)(depth < 1 ? 1 : depth) + 1; /* evaluations per chain and round, at most */
   int *phase = (int *)malloc(sizeof(int) * C), *left = (int *)malloc(sizeof(int) * C);
   int *tries = (int *)malloc(sizeof(int) * C), *chain = (int *)malloc(sizeof(int) * C * W);
@@ -128,12 +131,26 @@ static int slice_lockstep(double *xp, size_t C, const double *lo, const double *
   }
   for (;;) {
     /* the points this round evaluates */
+    size_t active = 0, seen = 0, base = 0, rem = 0;
+    if (slots) { /* the evaluations that fit into this round's waves beyond one per chain */
+      for (c = 0; c < C; c++) active += phase[c] != PH_DONE;
+      if (active) {
+        const size_t extra = (active + slots - 1) / slots * slots - active;
+        base = extra / active;
+        rem = extra % active;
+      }
+    }
     cnt = 0;
     for (c = 0; c < C; c++) {
       stb_rng48 r;
       double b0, b1;
-      int np, k, tr;
+      int np, k, tr, d = depth;
       if (phase[c] == PH_DONE) continue;
+      if (slots) {
+        const size_t mine = 1 + base + (seen < rem ? 1 : 0);
+        d = mine < (size_t)depth ? (int)mine : depth;
+        seen++;
+      }
       first[c] = cnt;
       r.x = rng[c]; /* a copy: the stream itself advances in the replay below */
       if (phase[c] == PH_NEED_Y) {
@@ -143,12 +160,12 @@ static int slice_lockstep(double *xp, size_t C, const double *lo, const double *
         b0 = lo[c];
         b1 = hi[c];
         tr = 1;
-        np = depth - 1;
+        np = d - 1;
       } else {
         b0 = r0[c];
         b1 = r1[c];
         tr = tries[c];
-        np = depth;
+        np = d;
       }
       if (np > TOOMANY - tr) np = TOOMANY - tr; /* the sequential sampler gives up there */
       for (k = 0; k < np; k++) {
@@ -334,6 +351,7 @@ int stb_arms_simple_batch(double *x, size_t C, const double *lo, const double *h
 /* ------------------------------------------------------------------------------------------ */
 /* samplea, batched                                                                            */
 /* ------------------------------------------------------------------------------------------ */
+#define A_SPECULATE 8 /* at most; only into table slots a round would leave empty (see slice_lockstep) */
 typedef struct {
   stb_sweep_t *sweep;
   stb_pstat_dev_t *ps;
@@ -397,7 +415,7 @@ static int samplea_batch_core(double *a, size_t C, int I, const int *K, const sc
                               stb_rand31_t *rnd, int loops, stb_sample_stats *st) {
   double *lo = NULL, *hi = NULL;
   uint32_t *nn = NULL, *tt = NULL;
-  size_t total = 0, cnt = 0, c;
+  size_t total = 0, cnt = 0, c, slots = 0;
   int i, k, maxn = 1, maxt = 1, rc = -1;
   unsigned Mx = 0, Nx = 0;
   ABatch ab;
@@ -408,9 +426,7 @@ static int samplea_batch_core(double *a, size_t C, int I, const int *K, const sc
   hi = (double *)malloc(sizeof(double) * C);
   nn = (uint32_t *)malloc(sizeof(uint32_t) * (total ? total : 1));
   tt = (uint32_t *)malloc(sizeof(uint32_t) * (total ? total : 1));
-  ab.ssum = (double *)malloc(sizeof(double) * C);
-  ab.lg = (double *)malloc(sizeof(double) * C);
-  if (!lo || !hi || !nn || !tt || !ab.ssum || !ab.lg) goto done;
+  if (!lo || !hi || !nn || !tt) goto done;
   /* bounds per chain, lib/samplea.c:161-177 and :217 */
   for (c = 0; c < C; c++) {
     double mid = a[c];
@@ -438,7 +454,12 @@ static int samplea_batch_core(double *a, size_t C, int I, const int *K, const sc
     ab.sweep = sweep_acquire(Nx, Mx);
   }
   if (!ab.sweep || stb_sweep_set_pairs(ab.sweep, nn, tt, cnt)) goto done;
-  ab.ps = stb_cuda_pstat_create(I, T, NULL, bpar, bpar_per_chain ? C * (size_t)I : (size_t)I, C);
+  /* a round evaluates at most one point per chain plus what its last wave of tables has room for */
+  slots = (size_t)stb_sweep_tables_in_flight(ab.sweep);
+  ab.ssum = (double *)malloc(sizeof(double) * (C + slots));
+  ab.lg = (double *)malloc(sizeof(double) * (C + slots));
+  if (!ab.ssum || !ab.lg) goto done;
+  ab.ps = stb_cuda_pstat_create(I, T, NULL, bpar, bpar_per_chain ? C * (size_t)I : (size_t)I, C + slots);
   if (!ab.ps) goto done;
   ab.bpar_per_chain = bpar_per_chain;
   ab.st = st;
@@ -450,7 +471,7 @@ static int samplea_batch_core(double *a, size_t C, int I, const int *K, const sc
         rc = 1 + (int)c;
       }
   } else
-    rc = slice_lockstep(a, C, lo, hi, rng, loops, aterms_batch, &ab, st, 1);
+    rc = slice_lockstep(a, C, lo, hi, rng, loops, aterms_batch, &ab, st, A_SPECULATE, slots);
 done:
   if (ab.sweep) sweep_release(ab.sweep, Nx, Mx);
   if (ab.ps) stb_cuda_pstat_destroy(ab.ps);
@@ -649,7 +670,7 @@ static int sampleb_batch_core(double *b, size_t C, int I, double shape, double s
         free(g2);
       }
     } else
-      rc = slice_lockstep(xs, cnt, lo, hi, r2, loops, bterms_batch, &bb, sp, B_SPECULATE);
+      rc = slice_lockstep(xs, cnt, lo, hi, r2, loops, bterms_batch, &bb, sp, B_SPECULATE, 0);
     if (st) {
       st->evals = sub.evals;
       st->rounds = sub.rounds;
