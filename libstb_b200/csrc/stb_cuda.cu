@@ -462,7 +462,14 @@ extern "C" int stb_cuda_partition(stb_dev_t *d, double a, const uint32_t *n, con
   }
   if (count == 0 || n_m == 0) return 0;
   // the nodes by decreasing n (counting sort; n <= capN was checked by the caller)
-  std::vector<uint32_t> order(count), start((size_t)d->capN + 2, 0);
+  std::vector<uint32_t> order, start;
+  try {
+    order.resize(count);
+    start.assign((size_t)d->capN + 2, 0);
+  } catch (...) {  // no exception crosses the C ABI
+    snprintf(g_err, sizeof g_err, "stb_cuda_partition: out of host memory");
+    return -1;
+  }
   for (size_t i = 0; i < count; i++) {
     if (n[i] > d->capN) {
       snprintf(g_err, sizeof g_err, "stb_cuda_partition: n beyond the table");
