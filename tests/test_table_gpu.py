@@ -75,6 +75,30 @@ def test_float_storage(flags):
     t.free()
 
 
+def test_float_table_at_config1_size_fresh_and_grown():
+    """S_FLOAT at the config-1 shape (the precision_test.c question): every stored cell is
+    the FP64 value rounded to float give or take one float ulp, and a table GROWN to that size by
+    look-ups equals the fresh one bit for bit (the reference's incremental float table drifts by up to
+    2.3e-7 because its column extension re-reads float-rounded rows, lib/stable.c:399-400; a growth here
+    refills the extent from FP64 state)."""
+    N, M, a = 10000, 1000, 0.5
+    fl = stb.S_STABLE | stb.S_UVTABLE | stb.S_FLOAT
+    fresh = stb.Table(N, M, N, M, a, fl)
+    grown = stb.Table(300, 60, N, M, a, fl)
+    for n, m in ((900, 200), (4000, 700), (N - 1, M - 1)):
+        grown.S(n, m), grown.V(n, m)
+    assert (grown.usedN, grown.usedM) == (N, M)
+    S, V = harness.oracle_tables(N, M, a)
+    for which, ref in ((0, S), (1, V)):
+        mask = harness.valid_mask(N, M, for_V=bool(which))
+        g = fresh.rows(which, 1, N)[:, :M]
+        assert np.array_equal(g[mask], grown.rows(which, 1, N)[:, :M][mask])
+        want = ref.astype(np.float32).astype(np.float64)
+        assert harness.close(g[mask], want[mask], 1.2e-7).all()
+        assert np.mean(g[mask] == want[mask]) > 0.99
+    fresh.free(), grown.free()
+
+
 def test_float_table_answers_the_first_column_in_fp64():
     """S_S(n,1) is S_S1(n) (lib/stable.c:946-947): FP64 also for S_FLOAT tables -- scalar call, batched
     gather and sweep gather alike."""
