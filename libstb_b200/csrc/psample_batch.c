@@ -388,9 +388,14 @@ static struct {
   unsigned N, M;
 } g_sweep_cache;
 
-void stb_release_caches(void) {
+static void sweep_cache_drop(void) {
   if (g_sweep_cache.w) stb_sweep_free(g_sweep_cache.w);
   g_sweep_cache.w = NULL;
+}
+
+void stb_release_caches(void) {
+  sweep_cache_drop();
+  stb_cuda_pstat_purge();
 }
 
 static stb_sweep_t *sweep_acquire(unsigned N, unsigned M) {
@@ -399,12 +404,12 @@ static stb_sweep_t *sweep_acquire(unsigned N, unsigned M) {
     g_sweep_cache.w = NULL;
     return w;
   }
-  stb_release_caches();
+  sweep_cache_drop();
   return stb_sweep_create(N, M, 0);
 }
 
 static void sweep_release(stb_sweep_t *w, unsigned N, unsigned M) {
-  stb_release_caches();
+  sweep_cache_drop();
   g_sweep_cache.w = w;
   g_sweep_cache.N = N;
   g_sweep_cache.M = M;

@@ -32,7 +32,7 @@ struct stb_pstat_dev {
   int I;
   uint32_t *dT, *dN;     // [I]
   double *dbpar;         // [I] or [C][I]
-  size_t bpar_elems;
+  size_t bpar_elems, bpar_cap;
   stb_zig_tables *dzig;
   // per-call staging: x, aux1, aux2, out (doubles), chain (ints), rng (u64)
   size_t cap;
@@ -126,7 +126,7 @@ __global__ void k_betaQ(const uint32_t *__restrict__ N, int I, const double *__r
   Q[c] = bad ? nan("") : q;
 }
 
-extern "C" void stb_cuda_pstat_destroy(stb_pstat_dev_t *p) {
+static void pstat_free(stb_pstat_dev_t *p) {
   if (!p) return;
   cudaSetDevice(p->device);
   if (p->stream) cudaStreamSynchronize(p->stream);
@@ -147,9 +147,68 @@ extern "C" void stb_cuda_pstat_destroy(stb_pstat_dev_t *p) {
   free(p);
 }
 
+/*
+ * One context is parked between calls (the larger one when two compete): an MCMC run calls samplea /
+ * sampleb once per sweep with the same shapes, and a dozen cudaMalloc / cudaFree plus a pinned
+ * allocation per call cost about as much as sampleb's evaluations.  stb_cuda_pstat_purge() frees it
+ * (stb_release_caches).  The samplers are not thread-safe, here as in the reference.
+ */
+static stb_pstat_dev_t *g_pstat_parked;
+
+extern "C" void stb_cuda_pstat_purge(void) {
+  pstat_free(g_pstat_parked);
+  g_pstat_parked = NULL;
+}
+
+extern "C" void stb_cuda_pstat_destroy(stb_pstat_dev_t *p) {
+  if (!p) return;
+  if (p->stream) {
+    cudaSetDevice(p->device);
+    cudaStreamSynchronize(p->stream);
+  }
+  if (g_pstat_parked && g_pstat_parked->cap >= p->cap) {
+    pstat_free(p);
+    return;
+  }
+  pstat_free(g_pstat_parked);
+  g_pstat_parked = p;
+}
+
+static int pstat_upload_u32(uint32_t **dst, const uint32_t *src, int I) {
+  if (!src) return 0;
+  if (!*dst) PCK(cudaMalloc(dst, (size_t)I * sizeof(uint32_t)));
+  PCK(cudaMemcpy(*dst, src, (size_t)I * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  return 0;
+}
+
 extern "C" stb_pstat_dev_t *stb_cuda_pstat_create(int I, const uint32_t *T, const uint32_t *N, const double *bpar,
                                                   size_t bpar_elems, size_t max_evals) {
   if (stb_cuda_device_count() <= 0) return NULL;
+  {
+    /* the parked context, when it fits: only the statistics are uploaded again */
+    stb_pstat_dev_t *q = g_pstat_parked;
+    int dev = -1;
+    if (q && cudaGetDevice(&dev) == cudaSuccess && dev == q->device && q->I == I && q->cap >= (max_evals ? max_evals : 1)) {
+      int bad = pstat_upload_u32(&q->dT, T, I) || pstat_upload_u32(&q->dN, N, I);
+      if (!bad && bpar && bpar_elems) {
+        if (bpar_elems > q->bpar_cap) {
+          cudaFree(q->dbpar);
+          q->dbpar = NULL;
+          q->bpar_cap = 0;
+          bad = cudaMalloc(&q->dbpar, bpar_elems * sizeof(double)) != cudaSuccess;
+          if (!bad) q->bpar_cap = bpar_elems;
+        }
+        if (!bad) bad = cudaMemcpy(q->dbpar, bpar, bpar_elems * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess;
+      }
+      if (!bad) {
+        q->bpar_elems = bpar_elems;
+        g_pstat_parked = NULL;
+        return q;
+      }
+      cudaGetLastError();
+      stb_cuda_pstat_purge(); /* and build a fresh one below */
+    }
+  }
   stb_pstat_dev_t *p = (stb_pstat_dev_t *)calloc(1, sizeof *p);
   if (!p) return NULL;
   p->I = I;
@@ -169,6 +228,7 @@ extern "C" stb_pstat_dev_t *stb_cuda_pstat_create(int I, const uint32_t *T, cons
   }
   if (e == cudaSuccess && bpar && bpar_elems) {
     e = cudaMalloc(&p->dbpar, bpar_elems * sizeof(double));
+    if (e == cudaSuccess) p->bpar_cap = bpar_elems;
     if (e == cudaSuccess) e = cudaMemcpy(p->dbpar, bpar, bpar_elems * sizeof(double), cudaMemcpyHostToDevice);
   }
   if (e == cudaSuccess) {
@@ -184,7 +244,7 @@ extern "C" stb_pstat_dev_t *stb_cuda_pstat_create(int I, const uint32_t *T, cons
   if (e == cudaSuccess) e = cudaHostAlloc(&p->hbuf, 4 * p->cap * sizeof(double), cudaHostAllocDefault);
   if (e != cudaSuccess) {
     stb_cuda_set_error("stb_cuda_pstat_create", (int)e);
-    stb_cuda_pstat_destroy(p);
+    pstat_free(p);
     return NULL;
   }
   return p;

@@ -124,7 +124,8 @@ int stb_cuda_sweep_tables_in_flight(const stb_sweep_dev_t *w);
 typedef struct stb_pstat_dev stb_pstat_dev_t;
 stb_pstat_dev_t *stb_cuda_pstat_create(int I, const uint32_t *T, const uint32_t *N, const double *bpar,
                                        size_t bpar_elems, size_t max_evals);
-void stb_cuda_pstat_destroy(stb_pstat_dev_t *p);
+void stb_cuda_pstat_destroy(stb_pstat_dev_t *p); /* parks the context for the next create of the same shape */
+void stb_cuda_pstat_purge(void);                  /* frees the parked context */
 /* out[j] = sum_i [T_i log x_j + lgamma(T_i + b_i/x_j) - lgamma(b_i/x_j)], b row = chain[j] if per chain */
 int stb_cuda_pstat_aterms_lg(stb_pstat_dev_t *p, const double *x, const int *chain, size_t cnt, int bpar_per_chain,
                              double *out, float *ms);
