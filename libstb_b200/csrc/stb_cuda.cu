@@ -542,6 +542,13 @@ struct stb_sweep_dev {
   size_t npairs, pairs_cap, gather_cap;
   double *d_gather;    // [T][npairs], allocated when a gather is first asked for
   double *d_partial;   // [T][nblk]
+  // the DISTINCT pairs in cell order with their multiplicities (built on the device by set_pairs when
+  // every pair names a stored cell): what the sums-only runs gather -- fewer, address-ordered reads
+  unsigned *d_cnt;     // [N][ld] multiplicity per cell (scratch of the build)
+  unsigned *d_blkoff;  // per 256-cell block: distinct pairs before it; [nblocks] = total
+  uint32_t *d_un, *d_um;
+  double *d_uw;
+  size_t nuniq, uniq_cap;
   double *d_sum;       // [stage_cap]: one sum per table of a run
   double *h_stage;     // pinned staging for the sums of a whole run
   int *h_flags;        // pinned: watchdog flag of every wave of a run
@@ -552,8 +559,9 @@ struct stb_sweep_dev {
 template <typename T>
 __global__ void sweep_gather_kernel(const T *__restrict__ slabs, const double *__restrict__ s1s, size_t slab_elems,
                                     size_t ld, unsigned N, unsigned M,
-                                    const uint32_t *__restrict__ n, const uint32_t *__restrict__ m, size_t npairs,
-                                    double *__restrict__ gather, double *__restrict__ partial) {
+                                    const uint32_t *__restrict__ n, const uint32_t *__restrict__ m,
+                                    const double *__restrict__ wt, size_t npairs, double *__restrict__ gather,
+                                    double *__restrict__ partial) {
   __shared__ double red[256];
   const int tb = blockIdx.y;
   const T *tab = slabs + (size_t)tb * slab_elems;
@@ -570,6 +578,7 @@ __global__ void sweep_gather_kernel(const T *__restrict__ slabs, const double *_
     else
       v = (double)tab[(size_t)(nn - 1) * ld + (mm - 1)];
     if (gather) gather[(size_t)tb * npairs + i] = v;
+    if (wt) v *= wt[i];  // a distinct pair stands for wt of the caller's
   }
   red[threadIdx.x] = v;
   __syncthreads();
@@ -578,6 +587,71 @@ __global__ void sweep_gather_kernel(const T *__restrict__ slabs, const double *_
     __syncthreads();
   }
   if (threadIdx.x == 0) partial[(size_t)tb * gridDim.x + blockIdx.x] = red[0];
+}
+
+/* ---- distinct pairs with multiplicities, in cell order (deterministic: no atomics decide an order) ---- */
+__global__ void pair_count_kernel(const uint32_t *__restrict__ n, const uint32_t *__restrict__ m, size_t npairs, size_t ld,
+                                  unsigned *__restrict__ cnt) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npairs) return;
+  const unsigned nn = n[i], mm = m[i];
+  if (nn != mm) atomicAdd(&cnt[(size_t)(nn - 1) * ld + (mm - 1)], 1u);  // S^n_n = 1 adds nothing to a sum
+}
+__global__ void cell_count_kernel(const unsigned *__restrict__ cnt, size_t cells, unsigned *__restrict__ blkcnt) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  const int c = __syncthreads_count(i < cells && cnt[i] != 0);
+  if (threadIdx.x == 0) blkcnt[blockIdx.x] = (unsigned)c;
+}
+/* exclusive scan of nb block counts in place, total at [nb]; one block of 1024 threads */
+__global__ void blk_scan_kernel(unsigned *__restrict__ blk, unsigned nb) {
+  __shared__ unsigned part[1024];
+  const unsigned per = (nb + 1023u) / 1024u, b0 = threadIdx.x * per, b1 = min(nb, b0 + per);
+  unsigned s = 0;
+  for (unsigned b = b0; b < b1; b++) s += blk[b];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned run = 0;
+    for (int t = 0; t < 1024; t++) {
+      const unsigned v = part[t];
+      part[t] = run;
+      run += v;
+    }
+    blk[nb] = run;
+  }
+  __syncthreads();
+  unsigned run = part[threadIdx.x];
+  for (unsigned b = b0; b < b1; b++) {
+    const unsigned v = blk[b];
+    blk[b] = run;
+    run += v;
+  }
+}
+__global__ void cell_compact_kernel(const unsigned *__restrict__ cnt, size_t cells, size_t ld,
+                                    const unsigned *__restrict__ blkoff, uint32_t *__restrict__ un,
+                                    uint32_t *__restrict__ um, double *__restrict__ uw) {
+  __shared__ unsigned wbase[8];
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  const unsigned c = i < cells ? cnt[i] : 0u;
+  const unsigned ball = __ballot_sync(0xffffffffu, c != 0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) wbase[warp] = __popc(ball);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned run = 0;
+    for (int w = 0; w < 8; w++) {
+      const unsigned v = wbase[w];
+      wbase[w] = run;
+      run += v;
+    }
+  }
+  __syncthreads();
+  if (c != 0) {
+    const unsigned pos = blkoff[blockIdx.x] + wbase[warp] + __popc(ball & ((1u << lane) - 1u));
+    un[pos] = (uint32_t)(i / ld) + 1u;
+    um[pos] = (uint32_t)(i % ld) + 1u;
+    uw[pos] = (double)c;
+  }
 }
 
 __global__ void sweep_sum_kernel(const double *__restrict__ partial, int nblk, double *__restrict__ sum) {
@@ -602,6 +676,11 @@ extern "C" void stb_cuda_sweep_destroy(stb_sweep_dev_t *w) {
   cudaFree(w->s1);
   cudaFree(w->d_n);
   cudaFree(w->d_m);
+  cudaFree(w->d_cnt);
+  cudaFree(w->d_blkoff);
+  cudaFree(w->d_un);
+  cudaFree(w->d_um);
+  cudaFree(w->d_uw);
   cudaFree(w->d_gather);
   cudaFree(w->d_partial);
   cudaFree(w->d_sum);
@@ -676,6 +755,42 @@ extern "C" int stb_cuda_sweep_set_pairs(stb_sweep_dev_t *w, const uint32_t *n, c
   }
   CK(cudaMemcpyAsync(w->d_n, n, npairs * sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
   CK(cudaMemcpyAsync(w->d_m, m, npairs * sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
+  // Sums-only runs gather the DISTINCT pairs, in cell order, each weighted by how often it occurs
+  // (sampler statistics repeat: config 4 has 94 000 pairs on 58 752 cells).  Only when every pair
+  // names a stored cell; a pair outside the table keeps the plain list (its look-up answers -inf).
+  w->nuniq = 0;
+  bool all_in = true;
+  for (size_t i = 0; i < npairs && all_in; i++) all_in = !(m[i] == 0 || n[i] < m[i] || n[i] > w->N || m[i] > w->M);
+  if (all_in) {
+    const size_t cells = (size_t)w->N * w->ld;
+    const unsigned nb = (unsigned)((cells + 255) / 256);
+    if (!w->d_cnt) {
+      CK(cudaMalloc(&w->d_cnt, cells * sizeof(unsigned)));
+      CK(cudaMalloc(&w->d_blkoff, ((size_t)nb + 1) * sizeof(unsigned)));
+    }
+    if (npairs > w->uniq_cap) {
+      cudaFree(w->d_un);
+      cudaFree(w->d_um);
+      cudaFree(w->d_uw);
+      w->d_un = w->d_um = NULL;
+      w->d_uw = NULL;
+      w->uniq_cap = 0;
+      CK(cudaMalloc(&w->d_un, npairs * sizeof(uint32_t)));
+      CK(cudaMalloc(&w->d_um, npairs * sizeof(uint32_t)));
+      CK(cudaMalloc(&w->d_uw, npairs * sizeof(double)));
+      w->uniq_cap = npairs;
+    }
+    CK(cudaMemsetAsync(w->d_cnt, 0, cells * sizeof(unsigned), w->stream));
+    pair_count_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, w->stream>>>(w->d_n, w->d_m, npairs, w->ld, w->d_cnt);
+    cell_count_kernel<<<nb, 256, 0, w->stream>>>(w->d_cnt, cells, w->d_blkoff);
+    blk_scan_kernel<<<1, 1024, 0, w->stream>>>(w->d_blkoff, nb);
+    cell_compact_kernel<<<nb, 256, 0, w->stream>>>(w->d_cnt, cells, w->ld, w->d_blkoff, w->d_un, w->d_um, w->d_uw);
+    CK(cudaGetLastError());
+    unsigned total = 0;
+    CK(cudaMemcpyAsync(&total, w->d_blkoff + nb, sizeof(unsigned), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    w->nuniq = total;  // 0 (every pair on the diagonal): the plain list is used
+  }
   CK(cudaStreamSynchronize(w->stream));
   return 0;
 }
@@ -685,7 +800,7 @@ extern "C" int stb_cuda_sweep_run(stb_sweep_dev_t *w, const double *a, size_t na
   CK(cudaSetDevice(w->device));
   const size_t es = w->is_float ? 4 : 8;
   const size_t slab_elems = (size_t)w->N * w->ld;
-  const int nblk = (int)((w->npairs + 255) / 256);
+  int nblk_run = 0;
   if ((gather_out || sum_out) && !w->npairs) {
     snprintf(g_err, sizeof g_err, "stb_cuda_sweep_run: no look-up pairs set");
     return -1;
@@ -748,18 +863,24 @@ extern "C" int stb_cuda_sweep_run(stb_sweep_dev_t *w, const double *a, size_t na
     int rc = stb::strip_fill(&w->strip, args, w->stream, w->ev1, g_err, sizeof g_err);
     if (rc) return rc;
     if (gather_out || sum_out) {
-      dim3 grid((unsigned)nblk, (unsigned)nt);
+      // sums only: the distinct pairs with their multiplicities
+      const bool uq = !gather_out && w->nuniq > 0 && !getenv("STB_SWEEP_PLAIN_PAIRS");
+      const size_t np = uq ? w->nuniq : w->npairs;
+      const uint32_t *pn = uq ? w->d_un : w->d_n, *pm = uq ? w->d_um : w->d_m;
+      const double *pw = uq ? w->d_uw : NULL;
+      nblk_run = (int)((np + 255) / 256);
+      dim3 grid((unsigned)nblk_run, (unsigned)nt);
       if (w->is_float)
         sweep_gather_kernel<float><<<grid, 256, 0, w->stream>>>((const float *)w->slab, w->s1, slab_elems, w->ld, w->N, w->M,
-                                                                  w->d_n, w->d_m, w->npairs,
-                                                                  gather_out ? w->d_gather : NULL, w->d_partial);
+                                                                  pn, pm, pw, np, gather_out ? w->d_gather : NULL,
+                                                                  w->d_partial);
       else
         sweep_gather_kernel<double><<<grid, 256, 0, w->stream>>>((const double *)w->slab, w->s1, slab_elems, w->ld, w->N,
-                                                                   w->M, w->d_n, w->d_m, w->npairs,
-                                                                   gather_out ? w->d_gather : NULL, w->d_partial);
+                                                                   w->M, pn, pm, pw, np, gather_out ? w->d_gather : NULL,
+                                                                   w->d_partial);
       CK(cudaGetLastError());
       if (sum_out) {
-        sweep_sum_kernel<<<nt, 256, 0, w->stream>>>(w->d_partial, nblk, w->d_sum + j0);
+        sweep_sum_kernel<<<nt, 256, 0, w->stream>>>(w->d_partial, nblk_run, w->d_sum + j0);
         CK(cudaGetLastError());
       }
       if (gather_out) {
