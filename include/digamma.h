@@ -14,7 +14,7 @@ double MLdigamma(double x);   /* x > 0 */
 double MLtrigamma(double x);  /* x > 0 */
 double MLtetragamma(double x);  /* second derivative of psi, x > 0 */
 double MLpentagamma(double x);  /* third derivative of psi, x > 0 */
-double MLpsigamma(double x, double deriv); /* order round(deriv) in 0..3 (lib/polygamma.c:502-523); NaN beyond */
+double MLpsigamma(double x, double deriv); /* psi^(n)(x), n = round(deriv) >= 0 (lib/polygamma.c:502-523) */
 double digammaInv(double x);  /* Minka start + 5 Newton steps (lib/digammainv.c:27-38) */
 
 #define digamma(x) MLdigamma(x)

@@ -124,6 +124,20 @@ int stb_sampleb_batch(double *b, size_t C, int I, double shape, double scale, co
                       const double *apar, uint64_t *rng, int loops, stb_sample_stats *st);
 
 /*
+ * The same over several devices of this process (csrc/multi.c): chain c runs on devices[c % ndev], every
+ * device advances its chains with the single-device call at the same time, no traffic between devices;
+ * a[] / b[] / rng[] are updated in place.  devices == NULL or ndev <= 0: every visible device.  Chain c's
+ * draw and stream do not depend on the device list.  In *st the evaluations add up; rounds and eval_ms
+ * are the slowest device's; traces are not kept.
+ */
+int stb_samplea_batch_multi(const int *devices, int ndev, double *a, size_t C, int I, const int *K, const scnt_int *T,
+                            scnt_int **n, stcnt_int **t, const double *bpar, int bpar_per_chain, uint64_t *rng, int loops,
+                            stb_sample_stats *st);
+int stb_sampleb_batch_multi(const int *devices, int ndev, double *b, size_t C, int I, double shape, double scale,
+                            const scnt_int *N, const scnt_int *T, const double *apar, uint64_t *rng, int loops,
+                            stb_sample_stats *st);
+
+/*
  * The same in the reference's DEFAULT (ARS) configuration: every chain runs arms_simple(3, ...)
  * (lib/samplea.c:209-215 on [a - SQUEEZEA, a + SQUEEZEA] clipped to [A_MIN, A_MAX];
  * lib/sampleb.c:127-140 on [B_MIN, B_MAX]) as a resumable machine, the chains advance in lock-step

@@ -96,6 +96,27 @@ int stb_sweep_tables_in_flight(const stb_sweep_t *w);
 void stb_sweep_free(stb_sweep_t *w);
 
 /*
+ * Several devices from ONE process (csrc/multi.c).  The tables of a sweep are independent units -- the
+ * reference's unit of work is one S_remake per evaluation of samplea's log-posterior (lib/samplea.c:57-60) --
+ * so table j goes to devices[j % ndev]; every device runs the single-device engine on its share at the
+ * same time (one host thread per device for the duration of a call, no traffic between devices) and
+ * writes its results into row j of the caller's HOST arrays.  devices == NULL or ndev <= 0: every visible
+ * device.  A device may be named more than once (its shares then take turns on it).  The results equal
+ * the single-device results bit for bit, whatever the device list.  Arguments and return values as the
+ * single-device calls above; on failure stb_last_error() names the failing device.
+ */
+typedef struct stb_sweep_multi stb_sweep_multi_t;
+stb_sweep_multi_t *stb_sweep_multi_create(const int *devices, int ndev, unsigned N, unsigned M, uint32_t flags);
+int stb_sweep_multi_set_pairs(stb_sweep_multi_t *w, const uint32_t *n, const uint32_t *m, size_t npairs);
+int stb_sweep_multi_run(stb_sweep_multi_t *w, const double *a, size_t na, double *gather_out, double *sum_out,
+                        double *lastrow_out);
+/* device milliseconds of the most recent run: the slowest device's (they work side by side), one device's */
+double stb_sweep_multi_last_fill_ms(const stb_sweep_multi_t *w);
+double stb_sweep_multi_device_ms(const stb_sweep_multi_t *w, int g);
+int stb_sweep_multi_devices(const stb_sweep_multi_t *w);
+void stb_sweep_multi_free(stb_sweep_multi_t *w);
+
+/*
  * Per-chain replacement for the C library's rand() / srand() (glibc's additive feedback generator,
  * csrc/rand31.h): stb_rand31_seed(g, s) puts g in the state srand(s) puts the global generator in,
  * stb_rand31_next(g) returns what rand() would return next.  The batched ARS samplers draw each

@@ -60,6 +60,14 @@ def lib() -> C.CDLL:
     L.stb_sweep_last_fill_ms.restype, L.stb_sweep_last_fill_ms.argtypes = d, [vp]
     L.stb_sweep_tables_in_flight.restype, L.stb_sweep_tables_in_flight.argtypes = C.c_int, [vp]
     L.stb_sweep_free.restype, L.stb_sweep_free.argtypes = None, [vp]
+    L.stb_sweep_multi_create.restype = vp
+    L.stb_sweep_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, u, u, C.c_uint32]
+    L.stb_sweep_multi_set_pairs.restype, L.stb_sweep_multi_set_pairs.argtypes = C.c_int, [vp, u32p, u32p, C.c_size_t]
+    L.stb_sweep_multi_run.restype, L.stb_sweep_multi_run.argtypes = C.c_int, [vp, dp, C.c_size_t, dp, dp, dp]
+    L.stb_sweep_multi_last_fill_ms.restype, L.stb_sweep_multi_last_fill_ms.argtypes = d, [vp]
+    L.stb_sweep_multi_device_ms.restype, L.stb_sweep_multi_device_ms.argtypes = d, [vp, C.c_int]
+    L.stb_sweep_multi_devices.restype, L.stb_sweep_multi_devices.argtypes = C.c_int, [vp]
+    L.stb_sweep_multi_free.restype, L.stb_sweep_multi_free.argtypes = None, [vp]
     L.stb_release_caches.restype, L.stb_release_caches.argtypes = None, []
     # samplers (include/psample.h, srng.h, digamma.h)
     u64p, ip = C.POINTER(C.c_uint64), C.POINTER(C.c_int)
@@ -119,6 +127,10 @@ def lib() -> C.CDLL:
                                     C.POINTER(C.POINTER(C.c_uint16)), dp, C.c_int, u64p, C.c_int, vp]
     L.stb_sampleb_batch.restype = C.c_int
     L.stb_sampleb_batch.argtypes = [dp, C.c_size_t, C.c_int, d, d, u32p, u32p, dp, u64p, C.c_int, vp]
+    L.stb_samplea_batch_multi.restype = C.c_int
+    L.stb_samplea_batch_multi.argtypes = [ip, C.c_int] + L.stb_samplea_batch.argtypes
+    L.stb_sampleb_batch_multi.restype = C.c_int
+    L.stb_sampleb_batch_multi.argtypes = [ip, C.c_int] + L.stb_sampleb_batch.argtypes
     L.stb_last_fill_ms.restype, L.stb_last_fill_ms.argtypes = d, [vp]
     L.stb_last_partition_ms.restype, L.stb_last_partition_ms.argtypes = d, [vp]
     L.stb_device_table.restype, L.stb_device_table.argtypes = vp, [vp, C.c_int, C.POINTER(C.c_size_t)]
@@ -287,6 +299,60 @@ class Sweep:
             pass
 
 
+def _device_list(devices):
+    """(int*, ndev) for the multi-device entry points; None = every visible device"""
+    if devices is None:
+        return None, 0
+    arr = (C.c_int * len(devices))(*[int(x) for x in devices])
+    return arr, len(devices)
+
+
+class SweepMulti(Sweep):
+    """The sweep over several devices of this process (stb_sweep_multi_*): table j on devices[j % ndev]."""
+
+    def __init__(self, N, M, devices=None, flags=0):
+        self._L = lib()
+        self.N, self.M = N, M
+        arr, nd = _device_list(devices)
+        self.w = self._L.stb_sweep_multi_create(arr, nd, N, M, flags)
+        if not self.w:
+            raise RuntimeError("stb_sweep_multi_create failed: " + self._L.stb_last_error().decode())
+        self.npairs = 0
+
+    def set_pairs(self, n, m):
+        n = np.ascontiguousarray(n, dtype=np.uint32)
+        m = np.ascontiguousarray(m, dtype=np.uint32)
+        u32p = C.POINTER(C.c_uint32)
+        if self._L.stb_sweep_multi_set_pairs(self.w, n.ctypes.data_as(u32p), m.ctypes.data_as(u32p), n.shape[0]):
+            raise RuntimeError("stb_sweep_multi_set_pairs failed: " + self._L.stb_last_error().decode())
+        self.npairs = n.shape[0]
+
+    def run(self, a, gather=True, sums=True, lastrow=False):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        dp = C.POINTER(C.c_double)
+        g = np.empty((a.shape[0], self.npairs)) if gather else None
+        s = np.empty(a.shape[0]) if sums else None
+        r = np.empty((a.shape[0], self.M)) if lastrow else None
+        ptr = lambda x: x.ctypes.data_as(dp) if x is not None else None
+        if self._L.stb_sweep_multi_run(self.w, a.ctypes.data_as(dp), a.shape[0], ptr(g), ptr(s), ptr(r)):
+            raise RuntimeError("stb_sweep_multi_run failed: " + self._L.stb_last_error().decode())
+        return g, s, r
+
+    @property
+    def last_fill_ms(self): return self._L.stb_sweep_multi_last_fill_ms(self.w)
+    @property
+    def ndev(self): return self._L.stb_sweep_multi_devices(self.w)
+    @property
+    def device_ms(self): return [self._L.stb_sweep_multi_device_ms(self.w, g) for g in range(self.ndev)]
+    @property
+    def tables_in_flight(self): raise AttributeError("per device: see Sweep.tables_in_flight")
+
+    def free(self):
+        if self.w:
+            self._L.stb_sweep_multi_free(self.w)
+            self.w = None
+
+
 class SampleStats(C.Structure):
     """stb_sample_stats of include/psample.h."""
 
@@ -327,32 +393,34 @@ def _stats(C_chains, trace_cap):
     return st, keep
 
 
-def samplea_batch(a, counts, bpar, rng, loops=1, bpar_per_chain=False, trace_cap=0):
-    """stb_samplea_batch: returns (a_new, rng_new, stats dict)."""
+def samplea_batch(a, counts, bpar, rng, loops=1, bpar_per_chain=False, trace_cap=0, devices=False):
+    """stb_samplea_batch (devices=False) or stb_samplea_batch_multi (devices = a list of device ordinals, or
+    None for every visible device): returns (a_new, rng_new, stats dict)."""
     L = lib()
     a = np.array(a, dtype=np.float64)
     rng = np.array(rng, dtype=np.uint64)
     bpar = np.ascontiguousarray(bpar, dtype=np.float64)
-    st, keep = _stats(a.shape[0], trace_cap)
+    st, keep = _stats(a.shape[0], trace_cap if devices is False else 0)
     dp, u64p = C.POINTER(C.c_double), C.POINTER(C.c_uint64)
-    rc = L.stb_samplea_batch(a.ctypes.data_as(dp), a.shape[0], *counts.args(), bpar.ctypes.data_as(dp),
-                             int(bpar_per_chain), rng.ctypes.data_as(u64p), loops, C.byref(st))
+    args = (a.ctypes.data_as(dp), a.shape[0], *counts.args(), bpar.ctypes.data_as(dp), int(bpar_per_chain),
+            rng.ctypes.data_as(u64p), loops, C.byref(st))
+    rc = L.stb_samplea_batch(*args) if devices is False else L.stb_samplea_batch_multi(*_device_list(devices), *args)
     if rc:
         raise RuntimeError(f"stb_samplea_batch failed ({rc}): " + L.stb_last_error().decode())
     return a, rng, {"evals": st.evals, "rounds": st.rounds, "eval_ms": st.eval_ms, "trace": keep}
 
 
-def sampleb_batch(b, counts, shape, scale, apar, rng, loops=1, trace_cap=0):
-    """stb_sampleb_batch: returns (b_new, rng_new, stats dict)."""
+def sampleb_batch(b, counts, shape, scale, apar, rng, loops=1, trace_cap=0, devices=False):
+    """stb_sampleb_batch / stb_sampleb_batch_multi (see samplea_batch): returns (b_new, rng_new, stats dict)."""
     L = lib()
     b = np.array(b, dtype=np.float64)
     rng = np.array(rng, dtype=np.uint64)
     apar = np.ascontiguousarray(apar, dtype=np.float64)
-    st, keep = _stats(b.shape[0], trace_cap)
+    st, keep = _stats(b.shape[0], trace_cap if devices is False else 0)
     dp, u64p, u32p = C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
-    rc = L.stb_sampleb_batch(b.ctypes.data_as(dp), b.shape[0], counts.I, shape, scale, counts.N.ctypes.data_as(u32p),
-                             counts.T.ctypes.data_as(u32p), apar.ctypes.data_as(dp), rng.ctypes.data_as(u64p), loops,
-                             C.byref(st))
+    args = (b.ctypes.data_as(dp), b.shape[0], counts.I, shape, scale, counts.N.ctypes.data_as(u32p),
+            counts.T.ctypes.data_as(u32p), apar.ctypes.data_as(dp), rng.ctypes.data_as(u64p), loops, C.byref(st))
+    rc = L.stb_sampleb_batch(*args) if devices is False else L.stb_sampleb_batch_multi(*_device_list(devices), *args)
     if rc:
         raise RuntimeError(f"stb_sampleb_batch failed ({rc}): " + L.stb_last_error().decode())
     return b, rng, {"evals": st.evals, "rounds": st.rounds, "eval_ms": st.eval_ms, "trace": keep}

@@ -161,20 +161,53 @@ struct StripSmem {
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 /*
- * Warp-collective wait until *ctr >= need (shared-memory or global counter).  Shared-memory
- * counters and the data they guard are accessed in issue order by the SM, so volatile accesses
- * plus compiler barriers suffice inside a CTA; the global hand-off uses release/acquire.
+ * Memory ordering inside a CTA (PTX memory model, cta scope).  Every flag that hands data from one
+ * warp to another -- sb.progress, empty_gen[], BRing::written / taken -- is PUBLISHED with release
+ * semantics (release_cta(): the warp has synchronised, then one fence.acq_rel.cta in front of the flag
+ * store / reduction) and READ with ld.acquire.cta (an ordinary LDS in SASS: shared-memory accesses of a
+ * warp execute in order, so acquire costs nothing; release is one MEMBAR.ALL.CTA per 16-row batch in
+ * the producer and per 8 x 32 unit in a consumer).  The data itself moves with volatile accesses.
+ * Measured cost of the fences on config 2 (B200): S 8.80 -> 9.05 ms, S+V 13.25 -> 13.30, V 9.6 -> 11.0
+ * (a consumer's fence also waits for the acknowledgement of the unit's global stores).  Tried instead:
+ * the slot release as an mbarrier arrival (release semantics without a MEMBAR): S 9.26, V 10.6 with the
+ * producer's fence, 8.78 / 10.1 without -- no better; releasing the slot before the unit's stores: the
+ * fence then costs 0.04 ms but the kernel 0.4 ms more.  -DSTB_FENCES=0 builds the round-1 protocol
+ * (volatile accesses and compiler barriers only; development only).
+ */
+#ifndef STB_FENCES
+#define STB_FENCES 1
+#endif
+__device__ __forceinline__ void release_cta() {
+#if STB_FENCES
+  asm volatile("fence.acq_rel.cta;" ::: "memory");
+#else
+  asm volatile("" ::: "memory");
+#endif
+}
+__device__ __forceinline__ int ld_acquire_shared(const int *p) {
+  int v;
+#if STB_FENCES
+  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+#else
+  v = *(const volatile int *)p;
+#endif
+  return v;
+}
+
+/*
+ * Warp-collective wait until *ctr >= need (shared-memory counter: acquire at cta scope; global
+ * counter: relaxed polls, then an acq_rel fence at gpu scope).
  */
 template <bool GLOBAL, int SLEEP>
 __device__ __forceinline__ bool ctr_wait(const int *ctr, int need, int *abort_flag, int &cached) {
   if (cached >= need) return true;
-  int v = GLOBAL ? ld_relaxed_gpu(ctr) : ld_vol(ctr);
+  int v = GLOBAL ? ld_relaxed_gpu(ctr) : ld_acquire_shared(ctr);
   if (v < need) {
     const long long t0 = clock64();
     unsigned spins = 0;
     do {
       if (SLEEP) __nanosleep(SLEEP);
-      v = GLOBAL ? ld_relaxed_gpu(ctr) : ld_vol(ctr);
+      v = GLOBAL ? ld_relaxed_gpu(ctr) : ld_acquire_shared(ctr);
       if ((++spins & 1023u) == 0) {
         const int bad = ld_vol(abort_flag) || (clock64() - t0 > FILL_WATCHDOG);
         if (__any_sync(0xffffffffu, bad)) {
@@ -245,14 +278,23 @@ __device__ __forceinline__ double lds_f64(unsigned a) {
   asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
   return v;
 }
+/* flag words (acquire at cta scope: what the flag guards is ordered behind the load) */
 __device__ __forceinline__ int lds_s32(unsigned a) {
   int v;
+#if STB_FENCES
+  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+#else
   asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+#endif
   return v;
 }
 __device__ __forceinline__ int2 lds_v2s32(unsigned a) {
   int2 v;
+#if STB_FENCES
+  asm volatile("ld.acquire.cta.shared.s32 %0, [%2];\n\tld.acquire.cta.shared.s32 %1, [%2+4];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+#else
   asm volatile("ld.volatile.shared.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+#endif
   return v;
 }
 __device__ __forceinline__ void sts_s32_if(unsigned a, int v, bool pred) {
@@ -488,7 +530,7 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
     // ---- publish: ONE word says how far the ring is filled; consumers, flusher and loader work
     // out from it what they may touch ----
     __syncwarp();
-    asm volatile("" ::: "memory");
+    release_cta();
     sts_s32_if(a_prog, p, lane0);
     sts_s32_if(a_in_taken, p + g.delta, take_bnd);
     sts_s32_if(a_out_written, p, write_out);
@@ -516,6 +558,23 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
 #endif
 }
 
+
+// ---- table stores ---------------------------------------------------------------------------------------
+/*
+ * The consumers' table stores name the GLOBAL state space (st.global, not a generic store: the
+ * load/store unit need not resolve the address space).
+ */
+__device__ __forceinline__ unsigned long long gaddr(const void *p) { return (unsigned long long)__cvta_generic_to_global(p); }
+__device__ __forceinline__ unsigned long long row_addr(unsigned long long base, unsigned pitch_bytes, unsigned i) {
+  return base + (unsigned long long)(i * pitch_bytes);  // i * pitch is loop-invariant: kept in registers
+}
+__device__ __forceinline__ void stg(unsigned long long a, double v, double *) {
+  asm volatile("st.global.f64 [%0], %1;" ::"l"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ void stg(unsigned long long a, double v, float *) {
+  asm volatile("st.global.f32 [%0], %1;" ::"l"(a), "f"((float)v) : "memory");
+}
+
 // ---- consumer ----------------------------------------------------------------------------------------
 template <int K, int G, bool HAS_S, bool HAS_V, typename OutT>
 __device__ void strip_consumer(const StripParams &P, StripSub<K, G, HAS_V> &sb, const double *logtab,
@@ -529,6 +588,7 @@ __device__ void strip_consumer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
   OutT *tabV = (OutT *)tb.tabV;
   const bool first_strip = (g.rs == 0);
   const unsigned ld32 = (unsigned)P.ld;  // 8 rows x ld elements stay far below 2^32
+  const unsigned pitchb = ld32 * (unsigned)sizeof(OutT);  // row pitch in bytes (strip_fill checks ld * 8 < 2^32)
 
 #ifdef STB_PROFILE_PRODUCER
   long long cacc[4] = {0, 0, 0, 0};
@@ -587,9 +647,9 @@ __device__ void strip_consumer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
 #pragma unroll
           for (int i = 0; i < ST_RB; i++) v[i] = log_scaled_r<LOGTAB_REP8>(xv[i], (i >= thr) ? Eb : Ea, logtab);
           if (lane_ok) {
-            OutT *pS = tabS + cell0;
+            const unsigned long long gS = gaddr(tabS) + cell0 * sizeof(OutT);
 #pragma unroll
-            for (int i = 0; i < ST_RB; i++) st_out(pS + (size_t)((unsigned)i * ld32), v[i]);
+            for (int i = 0; i < ST_RB; i++) stg(row_addr(gS, pitchb, (unsigned)i), v[i], (OutT *)nullptr);
             if (first_strip && col == 0) {
 #pragma unroll
               for (int i = 0; i < ST_RB; i++) tb.s1[r0 + i] = v[i];
@@ -601,9 +661,9 @@ __device__ void strip_consumer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
 #pragma unroll
           for (int i = 0; i < ST_RB; i++) den[i] = (kq == 0) ? yc[i * 32] : xc[i * CP - 1];
           if (lane_ok && !(first_strip && col == 0)) {
-            OutT *pV = tabV + cell0;
+            const unsigned long long gV = gaddr(tabV) + cell0 * sizeof(OutT);
 #pragma unroll
-            for (int i = 0; i < ST_RB; i++) st_out(pV + (size_t)((unsigned)i * ld32), div_pos(xv[i], den[i]));
+            for (int i = 0; i < ST_RB; i++) stg(row_addr(gV, pitchb, (unsigned)i), div_pos(xv[i], den[i]), (OutT *)nullptr);
           }
         }
       } else if (lane_ok) {
@@ -627,8 +687,10 @@ __device__ void strip_consumer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
       }
     }
     __syncwarp();
-    asm volatile("" ::: "memory");
-    if (lane == 0) atomicAdd(&sb.empty_gen[slot], 1);
+    if (lane == 0) {
+      release_cta();  // the unit's ring reads are ordered in front of the slot's release
+      atomicAdd(&sb.empty_gen[slot], 1);
+    }
     ST_CTICK(2);  // the unit
     q += dq;
     kk += dk;
@@ -709,11 +771,11 @@ __device__ void strip_loader(const StripParams &P, BRing *ring, int delta, int l
     }
     if (got) {
       __syncwarp();
-      asm volatile("" ::: "memory");
+      release_cta();
       const int hi = next + got - 1;
       if (lane == 0) {
         st_vol(&ring->written, hi);
-        if (gb.taken && (hi - pub >= ST_NBG / 4 || hi == jlast)) st_vol(gb.taken, hi);
+        if (gb.taken && (hi - pub >= ST_NBG / 4 || hi == jlast)) st_release_gpu(gb.taken, hi);  // back-pressure: the entries were read
       }
       if (hi - pub >= ST_NBG / 4) pub = hi;
       next = hi + 1;
@@ -751,7 +813,7 @@ __device__ void strip_flusher(const StripParams &P, BRing *ring, int last, int l
       }
     }
     __syncwarp();
-    asm volatile("" ::: "memory");
+    release_cta();
     if (lane == 0) st_vol(&ring->taken, hi);
     next = hi + 1;
   }

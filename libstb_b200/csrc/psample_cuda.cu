@@ -20,6 +20,9 @@
 #include "rng48.h"
 #include "specfun.h"
 #include "stb_cuda.h"
+#include "dev_guard.cuh"
+
+#include <mutex>
 
 extern "C" const stb_zig_tables *stb_zig_tables_get(void);  // psample.c
 extern "C" const char *stb_cuda_last_error(void);
@@ -42,6 +45,12 @@ struct stb_pstat_dev {
   double *hbuf;  // pinned, 4*cap doubles
 };
 
+#define P_ON_DEVICE(dev)                                   \
+  stb::DeviceGuard dev_guard_(dev);                        \
+  if (dev_guard_.err != cudaSuccess) {                     \
+    stb_cuda_set_error("cudaSetDevice", (int)dev_guard_.err); \
+    return (int)dev_guard_.err;                            \
+  }
 #define PCK(call)                                        \
   do {                                                   \
     cudaError_t e_ = (call);                             \
@@ -128,7 +137,7 @@ __global__ void k_betaQ(const uint32_t *__restrict__ N, int I, const double *__r
 
 static void pstat_free(stb_pstat_dev_t *p) {
   if (!p) return;
-  cudaSetDevice(p->device);
+  stb::DeviceGuard dev_guard_(p->device);
   if (p->stream) cudaStreamSynchronize(p->stream);
   cudaFree(p->dT);
   cudaFree(p->dN);
@@ -148,30 +157,44 @@ static void pstat_free(stb_pstat_dev_t *p) {
 }
 
 /*
- * One context is parked between calls (the larger one when two compete): an MCMC run calls samplea /
- * sampleb once per sweep with the same shapes, and a dozen cudaMalloc / cudaFree plus a pinned
- * allocation per call cost about as much as sampleb's evaluations.  stb_cuda_pstat_purge() frees it
- * (stb_release_caches).  The samplers are not thread-safe, here as in the reference.
+ * One context per device is parked between calls (the larger one when two compete): an MCMC run calls
+ * samplea / sampleb once per sweep with the same shapes, and a dozen cudaMalloc / cudaFree plus a pinned
+ * allocation per call cost about as much as sampleb's evaluations.  stb_cuda_pstat_purge() frees them
+ * (stb_release_caches).  The parking slots are guarded by a mutex: the multi-device entry points run one
+ * sampler per device concurrently (a context in use is never in a slot).
  */
-static stb_pstat_dev_t *g_pstat_parked;
+#define STB_MAX_DEVICES 64
+static stb_pstat_dev_t *g_pstat_parked[STB_MAX_DEVICES];
+static std::mutex g_pstat_mutex;
+
+static stb_pstat_dev_t *pstat_park_take(int dev) {
+  if (dev < 0 || dev >= STB_MAX_DEVICES) return NULL;
+  std::lock_guard<std::mutex> lk(g_pstat_mutex);
+  stb_pstat_dev_t *q = g_pstat_parked[dev];
+  g_pstat_parked[dev] = NULL;
+  return q;
+}
 
 extern "C" void stb_cuda_pstat_purge(void) {
-  pstat_free(g_pstat_parked);
-  g_pstat_parked = NULL;
+  for (int dev = 0; dev < STB_MAX_DEVICES; dev++) pstat_free(pstat_park_take(dev));
 }
 
 extern "C" void stb_cuda_pstat_destroy(stb_pstat_dev_t *p) {
   if (!p) return;
   if (p->stream) {
-    cudaSetDevice(p->device);
+    stb::DeviceGuard dev_guard_(p->device);
     cudaStreamSynchronize(p->stream);
   }
-  if (g_pstat_parked && g_pstat_parked->cap >= p->cap) {
-    pstat_free(p);
-    return;
+  stb_pstat_dev_t *drop = p;
+  if (p->device >= 0 && p->device < STB_MAX_DEVICES) {
+    std::lock_guard<std::mutex> lk(g_pstat_mutex);
+    stb_pstat_dev_t *&slot = g_pstat_parked[p->device];
+    if (!slot || slot->cap < p->cap) {
+      drop = slot;
+      slot = p;
+    }
   }
-  pstat_free(g_pstat_parked);
-  g_pstat_parked = p;
+  pstat_free(drop);
 }
 
 static int pstat_upload_u32(uint32_t **dst, const uint32_t *src, int I) {
@@ -185,10 +208,10 @@ extern "C" stb_pstat_dev_t *stb_cuda_pstat_create(int I, const uint32_t *T, cons
                                                   size_t bpar_elems, size_t max_evals) {
   if (stb_cuda_device_count() <= 0) return NULL;
   {
-    /* the parked context, when it fits: only the statistics are uploaded again */
-    stb_pstat_dev_t *q = g_pstat_parked;
+    /* this device's parked context, when it fits: only the statistics are uploaded again */
     int dev = -1;
-    if (q && cudaGetDevice(&dev) == cudaSuccess && dev == q->device && q->I == I && q->cap >= (max_evals ? max_evals : 1)) {
+    stb_pstat_dev_t *q = cudaGetDevice(&dev) == cudaSuccess ? pstat_park_take(dev) : NULL;
+    if (q && q->I == I && q->cap >= (max_evals ? max_evals : 1)) {
       int bad = pstat_upload_u32(&q->dT, T, I) || pstat_upload_u32(&q->dN, N, I);
       if (!bad && bpar && bpar_elems) {
         if (bpar_elems > q->bpar_cap) {
@@ -202,12 +225,11 @@ extern "C" stb_pstat_dev_t *stb_cuda_pstat_create(int I, const uint32_t *T, cons
       }
       if (!bad) {
         q->bpar_elems = bpar_elems;
-        g_pstat_parked = NULL;
         return q;
       }
       cudaGetLastError();
-      stb_cuda_pstat_purge(); /* and build a fresh one below */
     }
+    pstat_free(q); /* does not fit (or failed): build a fresh one below */
   }
   stb_pstat_dev_t *p = (stb_pstat_dev_t *)calloc(1, sizeof *p);
   if (!p) return NULL;
@@ -258,7 +280,7 @@ static int stage_in(stb_pstat_dev_t *p, double *dst, const double *src, size_t c
 
 extern "C" int stb_cuda_pstat_aterms_lg(stb_pstat_dev_t *p, const double *x, const int *chain, size_t cnt,
                                         int bpar_per_chain, double *out, float *ms) {
-  PCK(cudaSetDevice(p->device));
+  P_ON_DEVICE(p->device);
   if (cnt > p->cap || !p->dT || !p->dbpar) {
     stb_cuda_set_error("stb_cuda_pstat_aterms_lg: bad call", -1);
     return -1;
@@ -279,7 +301,7 @@ extern "C" int stb_cuda_pstat_aterms_lg(stb_pstat_dev_t *p, const double *x, con
 
 extern "C" int stb_cuda_pstat_bterms(stb_pstat_dev_t *p, const double *x, const double *Q, const double *apar,
                                      double shape, size_t cnt, int digamma_sum, double *out, float *ms) {
-  PCK(cudaSetDevice(p->device));
+  P_ON_DEVICE(p->device);
   if (cnt > p->cap || !p->dT) {
     stb_cuda_set_error("stb_cuda_pstat_bterms: bad call", -1);
     return -1;
@@ -301,7 +323,7 @@ extern "C" int stb_cuda_pstat_bterms(stb_pstat_dev_t *p, const double *x, const 
 
 extern "C" int stb_cuda_pstat_betaQ(stb_pstat_dev_t *p, const double *b_in, uint64_t *rng, size_t C, double scale,
                                     double *Q, float *ms) {
-  PCK(cudaSetDevice(p->device));
+  P_ON_DEVICE(p->device);
   if (C > p->cap || !p->dN) {
     stb_cuda_set_error("stb_cuda_pstat_betaQ: bad call", -1);
     return -1;

@@ -80,6 +80,42 @@ STB_SF_HD double stb_pentagamma(double x) {
   return r + 2.0 * f * xi + 3.0 * f * f + t;
 }
 
+/*
+ * psi^(n)(x), x > 0, any order n >= 0 (MLpsigamma; lib/polygamma.c:502-523 evaluates Amos' algorithm 610 at
+ * any order): psi^(n)(x) = (-1)^(n+1) n! zeta(n+1, x), the Hurwitz zeta function by direct summation up to
+ * x + k >= 15 + n and the Euler-Maclaurin tail
+ *   zeta(s, X) = X^(1-s)/(s-1) + X^-s/2 + sum_j B_2j/(2j)! s(s+1)...(s+2j-2) X^-(s+2j-1).
+ * Orders 0..3 go to the dedicated series above.
+ */
+STB_SF_HD double stb_polygamma(int n, double x) {
+  const double b2j[7] = {1.0 / 6.0, -1.0 / 30.0, 1.0 / 42.0, -1.0 / 30.0, 5.0 / 66.0, -691.0 / 2730.0, 7.0 / 6.0};
+  double head = 0.0, s, xi, term, poch, fact2j, tail, nfact = 1.0;
+  int j, k;
+  if (n < 0) return NAN;
+  if (n == 0) return stb_digamma(x);
+  if (n == 1) return stb_trigamma(x);
+  if (n == 2) return stb_tetragamma(x);
+  if (n == 3) return stb_pentagamma(x);
+  s = (double)n + 1.0;
+  while (x < 15.0 + n) {
+    head += pow(x, -s);
+    x += 1.0;
+  }
+  xi = 1.0 / x;
+  tail = pow(x, 1.0 - s) / (s - 1.0) + 0.5 * pow(x, -s);
+  term = pow(x, -s) * xi; /* X^-(s+1) */
+  poch = s;               /* s (s+1) ... (s+2j-2) */
+  fact2j = 2.0;           /* (2j)! */
+  for (j = 1; j <= 7; j++) {
+    tail += b2j[j - 1] / fact2j * poch * term;
+    poch *= (s + 2.0 * j - 1.0) * (s + 2.0 * j);
+    fact2j *= (2.0 * j + 1.0) * (2.0 * j + 2.0);
+    term *= xi * xi;
+  }
+  for (k = 2; k <= n; k++) nfact *= (double)k;
+  return ((n & 1) ? 1.0 : -1.0) * nfact * (head + tail);
+}
+
 /* Neal's digamma as the reference's default build defines it (lib/digamma.c:31-48): recurrence
  * to x > 5, eight-term series */
 STB_SF_HD double stb_digammaRN(double x) {

@@ -27,24 +27,26 @@
 #include "stb_cuda.h"
 #include "yaps.h"
 
-/* rows per lazily fetched mirror block are chosen so that a block is about this many bytes */
+/* device slabs of tables whose maximum extent is at most this many bytes are allocated whole by S_make */
+#define PRESIZE_BYTES (64ull << 20)
+/* rows per mirror block are chosen so that a block is about this many bytes */
 #define MIRROR_BLOCK_BYTES (4u << 20)
-/* default limit (bytes of doubles, per table) under which the whole table is mirrored eagerly */
-#define MIRROR_EAGER_DEFAULT (1ull << 30)
 
 struct stb_table_impl {
   stb_dev_t *dev;
   int algo;
   size_t ld; /* elements per row, device and mirror alike */
-  /* eager mirrors: [usedN][ld] doubles in pinned memory (NULL when lazy) */
-  double *fullS, *fullV;
-  size_t full_elems;
-  /* lazy mirrors: one pinned block of blk_rows rows per slot, fetched on first touch */
+  /* Host mirror: pinned blocks of blk_rows rows, fetched from the device on first touch.  A refill does
+   * not free them: it only starts a new epoch, and a block whose epoch is old is fetched again when a
+   * look-up next lands in it -- a caller that alternates S_remake and a few look-ups (the samplers' loop,
+   * test/demo.c:467-488) pays for the rows it reads, not for pinning and copying the whole table. */
   unsigned blk_rows, nblk;
   double **blkS, **blkV;
+  uint32_t *epochS, *epochV; /* epoch the block's content belongs to (0: never fetched) */
+  uint32_t epoch;            /* of the current device content; bumped by every fill */
   /* S_THREADS (lib/stable.h:43, lib/stable.c:572-580): look-ups from several threads, growth
-   * serialised.  Growth here refills the table and drops the host mirror, so look-ups hold the
-   * lock shared while they read and growth holds it exclusively; fetching a lazy mirror block
+   * serialised.  Growth here refills the table and invalidates the host mirror, so look-ups hold the
+   * lock shared while they read and growth holds it exclusively; fetching a mirror block
    * (done under the shared lock) has its own mutex. */
   pthread_rwlock_t rw;
   pthread_mutex_t fetch_mutex;
@@ -71,71 +73,62 @@ static void rlock(stable_t *sp) { /* shared: reading cells */
 static void mirror_drop(stable_t *sp) {
   struct stb_table_impl *im = sp->impl;
   unsigned b;
-  stb_cuda_host_free(im->fullS);
-  stb_cuda_host_free(im->fullV);
-  im->fullS = im->fullV = NULL;
-  im->full_elems = 0;
   for (b = 0; b < im->nblk; b++) {
     if (im->blkS && im->blkS[b]) stb_cuda_host_free(im->blkS[b]);
     if (im->blkV && im->blkV[b]) stb_cuda_host_free(im->blkV[b]);
   }
   free(im->blkS);
   free(im->blkV);
+  free(im->epochS);
+  free(im->epochV);
   im->blkS = im->blkV = NULL;
+  im->epochS = im->epochV = NULL;
   im->nblk = 0;
 }
 
-static uint64_t mirror_eager_limit(void) {
-  const char *s = getenv("STB_MIRROR_EAGER_BYTES");
-  if (s && *s) return strtoull(s, NULL, 10);
-  return MIRROR_EAGER_DEFAULT;
-}
-
-/* (re)build the mirror bookkeeping after the device tables were (re)filled; 0 on success */
+/* after the device tables were (re)filled: every block is stale; the bookkeeping is rebuilt only when the
+ * extent or the row pitch changed (growth).  0 on success */
 static int mirror_reset(stable_t *sp) {
   struct stb_table_impl *im = sp->impl;
   const int hasS = (sp->flags & S_STABLE) != 0, hasV = (sp->flags & S_UVTABLE) != 0;
-  size_t elems;
+  const size_t ld = stb_cuda_table_ld(im->dev);
+  unsigned blk_rows = (unsigned)(MIRROR_BLOCK_BYTES / (ld * sizeof(double)));
+  unsigned nblk;
+  if (blk_rows < 1) blk_rows = 1;
+  nblk = (sp->usedN + blk_rows - 1) / blk_rows;
+  if (++im->epoch == 0) im->epoch = 1;
+  if (ld == im->ld && blk_rows == im->blk_rows && nblk == im->nblk && (!hasS || im->blkS) && (!hasV || im->blkV))
+    return 0; /* same geometry: the pinned blocks stay, their epochs are old now */
   mirror_drop(sp);
-  im->ld = stb_cuda_table_ld(im->dev);
-  elems = (size_t)sp->usedN * im->ld;
-  if (!(sp->flags & S_NOMIRROR) && (uint64_t)elems * sizeof(double) <= mirror_eager_limit()) {
-    if (hasS) {
-      im->fullS = (double *)stb_cuda_host_alloc(elems * sizeof(double));
-      if (!im->fullS || stb_cuda_read_rows(im->dev, STB_TAB_S, 0, sp->usedN, im->fullS)) return 1;
-    }
-    if (hasV) {
-      im->fullV = (double *)stb_cuda_host_alloc(elems * sizeof(double));
-      if (!im->fullV || stb_cuda_read_rows(im->dev, STB_TAB_V, 0, sp->usedN, im->fullV)) return 1;
-    }
-    im->full_elems = elems;
-    return 0;
-  }
-  im->blk_rows = (unsigned)(MIRROR_BLOCK_BYTES / (im->ld * sizeof(double)));
-  if (im->blk_rows < 1) im->blk_rows = 1;
-  im->nblk = (sp->usedN + im->blk_rows - 1) / im->blk_rows;
-  if (hasS && !(im->blkS = (double **)calloc(im->nblk, sizeof(double *)))) return 1;
-  if (hasV && !(im->blkV = (double **)calloc(im->nblk, sizeof(double *)))) return 1;
+  im->ld = ld;
+  im->blk_rows = blk_rows;
+  im->nblk = nblk;
+  if (hasS && (!(im->blkS = (double **)calloc(nblk, sizeof(double *))) || !(im->epochS = (uint32_t *)calloc(nblk, sizeof(uint32_t)))))
+    return 1;
+  if (hasV && (!(im->blkV = (double **)calloc(nblk, sizeof(double *))) || !(im->epochV = (uint32_t *)calloc(nblk, sizeof(uint32_t)))))
+    return 1;
   return 0;
 }
 
-/* slow path of a lazy read: bring one block of rows across; NULL on failure */
+/* slow path of a read: bring one block of rows across (again); NULL on failure */
 static double *mirror_fetch(stable_t *sp, int which, unsigned b) {
   struct stb_table_impl *im = sp->impl;
   double **tab = which == STB_TAB_S ? im->blkS : im->blkV;
+  uint32_t *ep = which == STB_TAB_S ? im->epochS : im->epochV;
   double *blk;
   if (im->locking) pthread_mutex_lock(&im->fetch_mutex);
   blk = tab[b];
-  if (!blk) {
+  if (!blk || __atomic_load_n(&ep[b], __ATOMIC_ACQUIRE) != im->epoch) {
     unsigned row0 = b * im->blk_rows, rows = im->blk_rows;
     if (row0 + rows > sp->usedN) rows = sp->usedN - row0;
-    blk = (double *)stb_cuda_host_alloc((size_t)im->blk_rows * im->ld * sizeof(double));
+    if (!blk) blk = (double *)stb_cuda_host_alloc((size_t)im->blk_rows * im->ld * sizeof(double));
     if (blk && stb_cuda_read_rows(im->dev, which, row0, rows, blk)) {
       stb_cuda_host_free(blk);
       blk = NULL;
     }
+    tab[b] = blk;
     /* publish only after the block is complete: readers are lock-free */
-    __atomic_store_n(&tab[b], blk, __ATOMIC_RELEASE);
+    if (blk) __atomic_store_n(&ep[b], im->epoch, __ATOMIC_RELEASE);
   }
   if (im->locking) pthread_mutex_unlock(&im->fetch_mutex);
   return blk;
@@ -147,17 +140,13 @@ static double cell(stable_t *sp, int which, unsigned n, unsigned m) {
   double v;
   rlock(sp);
   {
-    const double *full = which == STB_TAB_S ? im->fullS : im->fullV;
-    if (full)
-      v = full[(size_t)(n - 1) * im->ld + (m - 1)];
-    else {
-      double **tab = which == STB_TAB_S ? im->blkS : im->blkV;
-      unsigned b = (n - 1) / im->blk_rows;
-      double *blk = __atomic_load_n(&tab[b], __ATOMIC_ACQUIRE);
-      if (!blk && !(blk = mirror_fetch(sp, which, b)))
-        yaps_quit("stable: device read failed: %s\n", stb_cuda_last_error());
-      v = blk[(size_t)((n - 1) % im->blk_rows) * im->ld + (m - 1)];
-    }
+    double **tab = which == STB_TAB_S ? im->blkS : im->blkV;
+    const uint32_t *ep = which == STB_TAB_S ? im->epochS : im->epochV;
+    const unsigned b = (n - 1) / im->blk_rows;
+    double *blk = tab[b];
+    if (__atomic_load_n(&ep[b], __ATOMIC_ACQUIRE) != im->epoch && !(blk = mirror_fetch(sp, which, b)))
+      yaps_quit("stable: device read failed: %s\n", stb_cuda_last_error());
+    v = blk[(size_t)((n - 1) % im->blk_rows) * im->ld + (m - 1)];
   }
   unlock(sp);
   return v;
@@ -229,8 +218,17 @@ stable_t *S_make(unsigned initN, unsigned initM, unsigned maxN, unsigned maxM, d
   }
   sp->S1 = (double *)calloc(initN, sizeof(double));
   im->dev = stb_cuda_table_create((flags & S_STABLE) != 0, (flags & S_UVTABLE) != 0, (flags & S_FLOAT) != 0);
-  if (!sp->S1 || !im->dev || stb_cuda_table_reserve(im->dev, initN, initM, 0) ||
-      fill(sp, a, 0, 0, initN, initM)) {
+  if (im->dev) {
+    /* a table whose MAXIMUM extent is small gets all of it at once: it never reallocates when it grows */
+    const uint64_t es = (flags & S_FLOAT) ? 4 : 8, ntab = ((flags & S_STABLE) != 0) + ((flags & S_UVTABLE) != 0);
+    const uint64_t full = (uint64_t)maxN * (((uint64_t)maxM + 31) / 32 * 32) * es * ntab;
+    const int whole = full <= PRESIZE_BYTES;
+    if (stb_cuda_table_reserve(im->dev, whole ? maxN : initN, whole ? maxM : initM, 0)) {
+      stb_cuda_table_destroy(im->dev);
+      im->dev = NULL;
+    }
+  }
+  if (!sp->S1 || !im->dev || fill(sp, a, 0, 0, initN, initM)) {
     if (stb_cuda_last_error()[0]) yaps_message("S_make: %s\n", stb_cuda_last_error());
     S_free(sp);
     return NULL;
@@ -288,7 +286,9 @@ static int extend(stable_t *sp, unsigned Nreq, unsigned Mreq) {
     sp->S1 = s1;
     sp->usedN1 = (unsigned)N;
   }
-  if (stb_cuda_table_reserve(im->dev, (unsigned)N, (unsigned)M, 1) ||
+  /* the whole extent is refilled, so nothing of the old slab is kept; capacity doubles (within the table's
+   * maxima), so a table grown in 10 % steps -- lib/stable.c:590-601 -- reallocates a handful of times */
+  if (stb_cuda_table_grow(im->dev, (unsigned)N, (unsigned)M, sp->maxN, sp->maxM) ||
       fill(sp, sp->a, sp->usedN, sp->usedM, (unsigned)N, (unsigned)M))
     result = 1;
 done:
@@ -443,9 +443,7 @@ void S_free(stable_t *sp) {
 void S_report(stable_t *sp, FILE *fp) {
   const char *s = (sp->flags & S_STABLE) ? "+S" : "", *uv = (sp->flags & S_UVTABLE) ? "+U/V" : "";
   const char *ty = (sp->flags & S_FLOAT) ? "float" : "double";
-  uint64_t bytes = stb_cuda_table_bytes(sp->impl->dev) + (uint64_t)sp->usedN1 * sizeof(double) +
-                   (uint64_t)sp->impl->full_elems * sizeof(double) *
-                       (((sp->flags & S_STABLE) != 0) + ((sp->flags & S_UVTABLE) != 0));
+  uint64_t bytes = stb_cuda_table_bytes(sp->impl->dev) + (uint64_t)sp->usedN1 * sizeof(double);
   sp->memalloced = (uint32_t)bytes; /* the reference keeps a uint32 too (lib/stable.h:105) */
   if (fp) {
     if (sp->tag)

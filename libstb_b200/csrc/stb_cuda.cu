@@ -15,15 +15,21 @@
 #include <vector>
 
 #include "stb_cuda.h"
+#include "dev_guard.cuh"
 #include "fill_mirror.cuh"
 #include "fill_strip.cuh"
 
-static char g_err[512] = "";
+/* last error text, per thread: S_THREADS callers and the per-device worker threads of the multi-device
+ * entry points (multi.c) fail independently */
+static thread_local char g_err[512] = "";
 
 static int fail(cudaError_t e, const char *what) {
   snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
   return (int)e ? (int)e : -1;
 }
+#define ON_DEVICE(dev)              \
+  stb::DeviceGuard dev_guard_(dev); \
+  if (dev_guard_.err != cudaSuccess) return fail(dev_guard_.err, "cudaSetDevice")
 #define CK(call)                                   \
   do {                                             \
     cudaError_t e_ = (call);                       \
@@ -66,6 +72,21 @@ extern "C" int stb_cuda_device_count(void) {
 }
 
 extern "C" const char *stb_cuda_last_error(void) { return g_err; }
+
+extern "C" int stb_cuda_current_device(void) {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  return dev;
+}
+
+extern "C" int stb_cuda_use_device(int dev) {
+  cudaError_t e = cudaSetDevice(dev);
+  if (e != cudaSuccess) return fail(e, "cudaSetDevice");
+  return 0;
+}
 extern "C" void stb_cuda_set_error(const char *what, int code) {
   if (code > 0)
     snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString((cudaError_t)code));
@@ -96,7 +117,7 @@ extern "C" stb_dev_t *stb_cuda_table_create(int want_S, int want_V, int is_float
 
 extern "C" void stb_cuda_table_destroy(stb_dev_t *d) {
   if (!d) return;
-  cudaSetDevice(d->device);
+  stb::DeviceGuard dev_guard_(d->device);
   cudaStreamSynchronize(d->stream);
   cudaFree(d->S);
   cudaFree(d->V);
@@ -123,45 +144,100 @@ extern "C" size_t stb_cuda_table_bytes(const stb_dev_t *d) {
          d->scratch_elems * sizeof(double) + stb::strip_state_bytes(&d->strip);
 }
 
-extern "C" int stb_cuda_table_reserve(stb_dev_t *d, unsigned N, unsigned M, int keep) {
-  CK(cudaSetDevice(d->device));
-  if (N <= d->capN && M <= d->capM) return 0;
-  unsigned newN = N > d->capN ? N : d->capN;
-  unsigned newM = M > d->capM ? M : d->capM;
-  size_t newld = ((size_t)newM + 31) / 32 * 32;
-  size_t es = elem_size(d);
-  void *nS = NULL, *nV = NULL;
-  double *ns1 = NULL;
-  cudaError_t e = cudaSuccess;
-  if (d->has_S) e = cudaMalloc(&nS, (size_t)newN * newld * es);
-  if (e == cudaSuccess && d->has_V) e = cudaMalloc(&nV, (size_t)newN * newld * es);
-  if (e == cudaSuccess) e = cudaMalloc(&ns1, (size_t)newN * sizeof(double));
-  if (e != cudaSuccess) {
-    cudaFree(nS);
-    cudaFree(nV);
-    cudaFree(ns1);
-    return fail(e, "cudaMalloc(table slab)");
-  }
-  if (keep && d->capN) {
-    CK(cudaStreamSynchronize(d->stream));
-    if (d->has_S)
-      CK(cudaMemcpy2D(nS, newld * es, d->S, d->ld * es, (size_t)d->capM * es, d->capN,
-                      cudaMemcpyDeviceToDevice));
-    if (d->has_V)
-      CK(cudaMemcpy2D(nV, newld * es, d->V, d->ld * es, (size_t)d->capM * es, d->capN,
-                      cudaMemcpyDeviceToDevice));
-    CK(cudaMemcpy(ns1, d->s1, (size_t)d->capN * sizeof(double), cudaMemcpyDeviceToDevice));
-  }
+static void table_release(stb_dev_t *d) {
   cudaFree(d->S);
   cudaFree(d->V);
   cudaFree(d->s1);
-  d->S = nS;
-  d->V = nV;
-  d->s1 = ns1;
+  d->S = d->V = NULL;
+  d->s1 = NULL;
+  d->capN = d->capM = 0;
+  d->ld = 0;
+}
+
+/* fresh slabs for newN x newM (the old ones are gone by now); on failure the table holds nothing */
+static cudaError_t table_alloc(stb_dev_t *d, unsigned newN, unsigned newM) {
+  const size_t newld = ((size_t)newM + 31) / 32 * 32, es = elem_size(d);
+  cudaError_t e = cudaSuccess;
+  if (d->has_S) e = cudaMalloc(&d->S, (size_t)newN * newld * es);
+  if (e == cudaSuccess && d->has_V) e = cudaMalloc(&d->V, (size_t)newN * newld * es);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d->s1, (size_t)newN * sizeof(double));
+  if (e != cudaSuccess) {
+    table_release(d);
+    cudaGetLastError();
+    return e;
+  }
   d->capN = newN;
   d->capM = newM;
   d->ld = newld;
+  return cudaSuccess;
+}
+
+extern "C" int stb_cuda_table_reserve(stb_dev_t *d, unsigned N, unsigned M, int keep) {
+  ON_DEVICE(d->device);
+  if (N <= d->capN && M <= d->capM) return 0;
+  const unsigned newN = N > d->capN ? N : d->capN, newM = M > d->capM ? M : d->capM;
+  if (!keep || !d->capN) {  // nothing worth keeping: give the old slabs back first (never two generations at once)
+    CK(cudaStreamSynchronize(d->stream));
+    table_release(d);
+    cudaError_t e = table_alloc(d, newN, newM);
+    return e == cudaSuccess ? 0 : fail(e, "cudaMalloc(table slab)");
+  }
+  // keep the filled cells: new slabs beside the old ones, a pitched copy, then the old ones go
+  stb_dev_t old = *d;
+  d->S = d->V = NULL;
+  d->s1 = NULL;
+  cudaError_t e = table_alloc(d, newN, newM);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
+  const size_t es = elem_size(d);
+  if (e == cudaSuccess && d->has_S)
+    e = cudaMemcpy2D(d->S, d->ld * es, old.S, old.ld * es, (size_t)old.capM * es, old.capN, cudaMemcpyDeviceToDevice);
+  if (e == cudaSuccess && d->has_V)
+    e = cudaMemcpy2D(d->V, d->ld * es, old.V, old.ld * es, (size_t)old.capM * es, old.capN, cudaMemcpyDeviceToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d->s1, old.s1, (size_t)old.capN * sizeof(double), cudaMemcpyDeviceToDevice);
+  if (e != cudaSuccess) {  // back to the old generation, nothing leaks
+    cudaFree(d->S);
+    cudaFree(d->V);
+    cudaFree(d->s1);
+    d->S = old.S;
+    d->V = old.V;
+    d->s1 = old.s1;
+    d->capN = old.capN;
+    d->capM = old.capM;
+    d->ld = old.ld;
+    return fail(e, "stb_cuda_table_reserve(keep)");
+  }
+  cudaFree(old.S);
+  cudaFree(old.V);
+  cudaFree(old.s1);
   return 0;
+}
+
+/*
+ * Room for a table that GROWS to N x M and will be refilled as a whole (S_extend): nothing is copied, the
+ * old slabs are freed before the new ones are allocated, and the capacity at least doubles in the
+ * dimension that ran out (capped by the table's maxima) -- the reference's growth policy is +10 % per
+ * step (lib/stable.c:590-601): ~41 steps from 10 000 to 500 000 rows become 6 allocations.
+ */
+extern "C" int stb_cuda_table_grow(stb_dev_t *d, unsigned N, unsigned M, unsigned maxN, unsigned maxM) {
+  ON_DEVICE(d->device);
+  if (N <= d->capN && M <= d->capM) return 0;
+  unsigned newN = d->capN, newM = d->capM;
+  if (N > d->capN) {
+    const unsigned long long twice = 2ull * d->capN;
+    newN = (unsigned)(twice > N ? (twice < maxN ? twice : maxN) : N);
+    if (newN < N) newN = N;
+  }
+  if (M > d->capM) {
+    const unsigned long long twice = 2ull * d->capM;
+    newM = (unsigned)(twice > M ? (twice < maxM ? twice : maxM) : M);
+    if (newM < M) newM = M;
+  }
+  if (newM > newN) newM = newN > M ? newN : M;
+  CK(cudaStreamSynchronize(d->stream));
+  table_release(d);
+  cudaError_t e = table_alloc(d, newN, newM);
+  if (e != cudaSuccess && (newN > N || newM > M)) e = table_alloc(d, N, M);  // no room for the head start: the exact extent
+  return e == cudaSuccess ? 0 : fail(e, "cudaMalloc(table slab)");
 }
 
 extern "C" void *stb_cuda_table_ptr(stb_dev_t *d, int which) { return which == STB_TAB_S ? d->S : d->V; }
@@ -199,7 +275,7 @@ static int fill_mirror(stb_dev_t *d, double a, unsigned N, unsigned M, double *s
 
 extern "C" int stb_cuda_fill(stb_dev_t *d, double a, unsigned startN, unsigned startM, unsigned N,
                              unsigned M, int algo, double *s1_host) {
-  CK(cudaSetDevice(d->device));
+  ON_DEVICE(d->device);
   if (N > d->capN || M > d->capM || N < 1 || M < 1) {
     snprintf(g_err, sizeof g_err, "stb_cuda_fill: extent %ux%u exceeds reserved %ux%u", N, M, d->capN,
              d->capM);
@@ -239,7 +315,7 @@ extern "C" int stb_cuda_fill(stb_dev_t *d, double a, unsigned startN, unsigned s
 
 /* log S^n_1, n = 1..N, of the most recent fill (the strip kernel leaves the column in d->s1) */
 extern "C" int stb_cuda_read_s1(stb_dev_t *d, unsigned N, double *dst) {
-  CK(cudaSetDevice(d->device));
+  ON_DEVICE(d->device);
   if (!d->s1 || N > d->capN) {
     snprintf(g_err, sizeof g_err, "stb_cuda_read_s1: bad range");
     return -1;
@@ -250,7 +326,7 @@ extern "C" int stb_cuda_read_s1(stb_dev_t *d, unsigned N, double *dst) {
 }
 
 extern "C" int stb_cuda_read_rows(stb_dev_t *d, int which, unsigned row0, unsigned nrows, double *dst) {
-  CK(cudaSetDevice(d->device));
+  ON_DEVICE(d->device);
   const void *tab = which == STB_TAB_S ? d->S : d->V;
   if (!tab || row0 + nrows > d->capN) {
     snprintf(g_err, sizeof g_err, "stb_cuda_read_rows: bad range");
@@ -320,7 +396,7 @@ __global__ void gather_kernel(const T *__restrict__ tab, const double *__restric
 
 extern "C" int stb_cuda_gather(stb_dev_t *d, int which, double a, unsigned usedN, unsigned usedM, const uint32_t *n,
                                const uint32_t *m, double *out, size_t count, int on_device) {
-  CK(cudaSetDevice(d->device));
+  ON_DEVICE(d->device);
   const void *tab = which == STB_TAB_S ? d->S : d->V;
   if (!tab) {
     snprintf(g_err, sizeof g_err, "stb_cuda_gather: table not held");
@@ -455,7 +531,7 @@ __global__ void partition_kernel(const T *__restrict__ tab, const double *__rest
 
 extern "C" int stb_cuda_partition(stb_dev_t *d, double a, const uint32_t *n, const uint16_t *t, const double *logu,
                                   const uint32_t *off, size_t count, uint16_t *m_out, size_t n_m, int exact) {
-  CK(cudaSetDevice(d->device));
+  ON_DEVICE(d->device);
   if (!d->S || !d->s1) {
     snprintf(g_err, sizeof g_err, "stb_cuda_partition: S table not held");
     return -1;
@@ -670,7 +746,7 @@ __global__ void sweep_sum_kernel(const double *__restrict__ partial, int nblk, d
 
 extern "C" void stb_cuda_sweep_destroy(stb_sweep_dev_t *w) {
   if (!w) return;
-  cudaSetDevice(w->device);
+  stb::DeviceGuard dev_guard_(w->device);
   if (w->stream) cudaStreamSynchronize(w->stream);
   cudaFree(w->slab);
   cudaFree(w->s1);
@@ -737,7 +813,7 @@ extern "C" stb_sweep_dev_t *stb_cuda_sweep_create(unsigned N, unsigned M, int is
 extern "C" int stb_cuda_sweep_tables_in_flight(const stb_sweep_dev_t *w) { return w->T; }
 
 extern "C" int stb_cuda_sweep_set_pairs(stb_sweep_dev_t *w, const uint32_t *n, const uint32_t *m, size_t npairs) {
-  CK(cudaSetDevice(w->device));
+  ON_DEVICE(w->device);
   w->npairs = npairs;
   if (!npairs) return 0;
   if (npairs > w->pairs_cap) {  // buffers are kept across calls (a cached handle sees many pair sets)
@@ -797,7 +873,18 @@ extern "C" int stb_cuda_sweep_set_pairs(stb_sweep_dev_t *w, const uint32_t *n, c
 
 extern "C" int stb_cuda_sweep_run(stb_sweep_dev_t *w, const double *a, size_t na, double *gather_out, double *sum_out,
                                   double *lastrow_out, float *fill_ms) {
-  CK(cudaSetDevice(w->device));
+  return stb_cuda_sweep_run_dealt(w, a, na, 0, 1, gather_out, sum_out, lastrow_out, fill_ms);
+}
+
+/*
+ * The same for the share of a sweep that was dealt to this device: unit k of this run (k < na) is the
+ * caller's unit u(k) = first + k * stride -- its discount is a[u(k)], its results go to row u(k) of the
+ * caller's arrays.  (first, stride) = (0, 1) is the whole sweep on one device.
+ */
+extern "C" int stb_cuda_sweep_run_dealt(stb_sweep_dev_t *w, const double *a, size_t na, size_t first, size_t stride,
+                                        double *gather_out, double *sum_out, double *lastrow_out, float *fill_ms) {
+  ON_DEVICE(w->device);
+  auto unit = [first, stride](size_t k) { return first + k * stride; };
   const size_t es = w->is_float ? 4 : 8;
   const size_t slab_elems = (size_t)w->N * w->ld;
   int nblk_run = 0;
@@ -847,7 +934,7 @@ extern "C" int stb_cuda_sweep_run(stb_sweep_dev_t *w, const double *a, size_t na
       tabs[t].tabS = (char *)w->slab + (size_t)t * slab_elems * es;
       tabs[t].tabV = NULL;
       tabs[t].s1 = w->s1 + (size_t)t * w->N;
-      tabs[t].a = a[j0 + t];
+      tabs[t].a = a[unit(j0 + t)];
     }
     stb::StripFillArgs args;
     args.tables = tabs.data();
@@ -884,8 +971,13 @@ extern "C" int stb_cuda_sweep_run(stb_sweep_dev_t *w, const double *a, size_t na
         CK(cudaGetLastError());
       }
       if (gather_out) {
-        CK(cudaMemcpyAsync(gather_out + j0 * w->npairs, w->d_gather, (size_t)nt * w->npairs * sizeof(double),
-                           cudaMemcpyDeviceToHost, w->stream));
+        if (stride == 1)
+          CK(cudaMemcpyAsync(gather_out + unit(j0) * w->npairs, w->d_gather, (size_t)nt * w->npairs * sizeof(double),
+                             cudaMemcpyDeviceToHost, w->stream));
+        else
+          CK(cudaMemcpy2DAsync(gather_out + unit(j0) * w->npairs, stride * w->npairs * sizeof(double), w->d_gather,
+                               w->npairs * sizeof(double), w->npairs * sizeof(double), (size_t)nt, cudaMemcpyDeviceToHost,
+                               w->stream));
         CK(cudaStreamSynchronize(w->stream));
       }
     }
@@ -893,13 +985,13 @@ extern "C" int stb_cuda_sweep_run(stb_sweep_dev_t *w, const double *a, size_t na
       for (int t = 0; t < nt; t++) {
         const char *row = (const char *)w->slab + ((size_t)t * slab_elems + (size_t)(w->N - 1) * w->ld) * es;
         if (!w->is_float) {
-          CK(cudaMemcpyAsync(lastrow_out + (j0 + t) * w->M, row, (size_t)w->M * sizeof(double), cudaMemcpyDeviceToHost,
+          CK(cudaMemcpyAsync(lastrow_out + unit(j0 + t) * w->M, row, (size_t)w->M * sizeof(double), cudaMemcpyDeviceToHost,
                              w->stream));
         } else {
           std::vector<float> tmp(w->M);
           CK(cudaMemcpyAsync(tmp.data(), row, (size_t)w->M * sizeof(float), cudaMemcpyDeviceToHost, w->stream));
           CK(cudaStreamSynchronize(w->stream));
-          for (unsigned c = 0; c < w->M; c++) lastrow_out[(j0 + t) * w->M + c] = (double)tmp[c];
+          for (unsigned c = 0; c < w->M; c++) lastrow_out[unit(j0 + t) * w->M + c] = (double)tmp[c];
         }
       }
       CK(cudaStreamSynchronize(w->stream));
@@ -914,7 +1006,7 @@ extern "C" int stb_cuda_sweep_run(stb_sweep_dev_t *w, const double *a, size_t na
       return -2;
     }
   if (sum_out)
-    for (size_t j = 0; j < na; j++) sum_out[j] = w->h_stage[j];
+    for (size_t j = 0; j < na; j++) sum_out[unit(j)] = w->h_stage[j];
   if (fill_ms) CK(cudaEventElapsedTime(fill_ms, w->ev0, w->ev1));
   return 0;
 }

@@ -30,8 +30,13 @@ typedef struct stb_dev stb_dev_t;
 
 /* number of usable CUDA devices (0 when none / driver missing) */
 int stb_cuda_device_count(void);
-/* last CUDA error text for diagnostics (static storage) */
+/* last error text of the CALLING THREAD for diagnostics (thread-local storage) */
 const char *stb_cuda_last_error(void);
+/* the calling thread's current device (-1: none), and cudaSetDevice for it (0 on success): handles are
+ * created on the current device; every call on a handle runs on the handle's device and restores the
+ * caller's.  Used by the per-device worker threads of the multi-device entry points (multi.c). */
+int stb_cuda_current_device(void);
+int stb_cuda_use_device(int dev);
 
 /*
  * Create the device side of one table object on the current device.
@@ -46,6 +51,9 @@ void stb_cuda_table_destroy(stb_dev_t *d);
  * 128-byte boundary.  With keep!=0 the cells already filled survive a re-allocation.
  */
 int stb_cuda_table_reserve(stb_dev_t *d, unsigned N, unsigned M, int keep);
+/* room for a table that grows to N x M and is then refilled as a whole: nothing is kept, the old slabs are
+ * freed first, the capacity at least doubles (capped at maxN x maxM) */
+int stb_cuda_table_grow(stb_dev_t *d, unsigned N, unsigned M, unsigned maxN, unsigned maxM);
 size_t stb_cuda_table_ld(const stb_dev_t *d);
 size_t stb_cuda_table_bytes(const stb_dev_t *d); /* device bytes currently held */
 
@@ -113,6 +121,10 @@ int stb_cuda_sweep_set_pairs(stb_sweep_dev_t *w, const uint32_t *n, const uint32
  */
 int stb_cuda_sweep_run(stb_sweep_dev_t *w, const double *a, size_t na, double *gather_out, double *sum_out,
                        double *lastrow_out, float *fill_ms);
+/* the share of a sweep dealt to this device: unit k < na of the run is the caller's unit first + k*stride
+ * (its discount a[first + k*stride], its results in that row of the caller's arrays) */
+int stb_cuda_sweep_run_dealt(stb_sweep_dev_t *w, const double *a, size_t na, size_t first, size_t stride,
+                             double *gather_out, double *sum_out, double *lastrow_out, float *fill_ms);
 /* tables one launch fills side by side for this extent on this device */
 int stb_cuda_sweep_tables_in_flight(const stb_sweep_dev_t *w);
 

@@ -134,7 +134,21 @@ def test_polygamma_golden():
             assert abs(got - dec(want)) <= 1e-12 * abs(dec(want)) + 1e-15, (x, got, want)
         for k, want in enumerate((d0, d1, d2, d3)):
             assert L.MLpsigamma(x, float(k)) == (L.MLdigamma, L.MLtrigamma, L.MLtetragamma, L.MLpentagamma)[k](x)
-    assert math.isnan(L.MLpsigamma(1.0, 7.0))
+    # orders beyond 3 (the reference's Amos 610 code serves any order, lib/polygamma.c:502-523): Hurwitz zeta form
+    from scipy.special import polygamma
+
+    for n in (4, 5, 7, 10):
+        for x in (0.3, 1.0, 2.5, 17.0, 123.4):
+            want = float(polygamma(n, x))
+            assert abs(L.MLpsigamma(x, float(n)) - want) <= 1e-12 * abs(want), (n, x)
+    if os.path.exists(harness.REF_SLICE_SO):  # and the reference itself (its polygamma.c is in the slice build)
+        R = C.CDLL(harness.REF_SLICE_SO)
+        R.MLpsigamma.restype, R.MLpsigamma.argtypes = C.c_double, [C.c_double, C.c_double]
+        for n in (4, 6):
+            for x in (0.7, 2.5, 40.0):
+                want = R.MLpsigamma(x, float(n))
+                assert abs(L.MLpsigamma(x, float(n)) - want) <= 1e-10 * abs(want), (n, x, want)
+    assert math.isnan(L.MLpsigamma(1.0, -1.0))
 
 
 @pytest.mark.skipif(not os.path.exists(harness.REF_SLICE_SO), reason="reference build not present")

@@ -16,6 +16,7 @@ using namespace stb;
 template <int K, int CP, int MODE>
 __device__ __forceinline__ void steps_var(double (&x)[K], const double (&ma)[K], double &nm1, double &yin, const double scn,
                                           unsigned &nb_addr, const unsigned nb_stride, const unsigned xr) {
+  double xp[K];
 #pragma unroll
   for (int i = 0; i < ST_RB; i++) {
     double nb = 1.0;
@@ -28,8 +29,28 @@ __device__ __forceinline__ void steps_var(double (&x)[K], const double (&ma)[K],
     x[0] = fma((MODE & 4) ? ma[0] : nm1 - ma[0], x[0], yin);
     nm1 += 1.0;
     if (!(MODE & 1)) {
+      if (MODE & 8) {  // 16-byte stores, K even
 #pragma unroll
-      for (int k = 0; k < K; k++) sts_f64(xr + (i * CP + k) * 8, x[k]);
+        for (int k = 0; k < K; k += 2)
+          asm volatile("st.volatile.shared.v2.f64 [%0], {%1,%2};" ::"r"(xr + (i * CP + k) * 8), "d"(x[k]), "d"(x[k + 1 < K ? k + 1 : k]));
+      } else if (MODE & 16) {  // columns 0..K-2: one 16-byte store per column and PAIR of rows; column K-1 every row
+        sts_f64(xr + (i * CP + K - 1) * 8, x[K - 1]);
+        if (i & 1) {
+#pragma unroll
+          for (int k = 0; k < K - 1; k++)
+            asm volatile("st.volatile.shared.v2.f64 [%0], {%1,%2};" ::"r"(xr + ((i - 1) * CP + 2 * k) * 8 + 16 * 1024), "d"(xp[k]), "d"(x[k]));
+        } else {
+#pragma unroll
+          for (int k = 0; k < K - 1; k++) xp[k] = x[k];
+        }
+      } else if (MODE & 32) {  // weak (non-volatile) stores
+#pragma unroll
+        for (int k = 0; k < K; k++) asm volatile("st.shared.f64 [%0], %1;" ::"r"(xr + (i * CP + k) * 8), "d"(x[k]) : "memory");
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; k++) sts_f64(xr + (i * CP + k) * 8, x[k]);
+      }
+      if (MODE & 64) sts_f64_if(xr + 64 * 1024 + i * 8, x[K - 1], (threadIdx.x & 31) == 31);  // the boundary column's extra store
     }
     yin = nb * scn;
   }
@@ -65,7 +86,7 @@ __global__ void steps_kernel(long long *cycles, double *sink, int batches, doubl
     if (lane == 0) sE = elow;
     const double scn = lane == 0 ? 0.0 : pow2i(sE - elow);
     unsigned nb_addr = lane == 0 ? a_out + 8u : a_xr - 8u;
-    if (MODE == 0) {
+    if (MODE == 0) {  // MODE 128: steps_var with everything on
       strip_steps<K, false, false, CP, RS, true>(x, ma, nm1, yin, lane == 0 ? a_out : a_xr + 15 * CP * 8 - 8u, scn, scn, nb_addr, nb_stride, lane == 31, a_xr, a_yr, a_out);
       strip_steps<K, false, false, CP, RS, false>(x, ma, nm1, yin, 0u, scn, scn, nb_addr, nb_stride, lane == 31, a_xr + 8 * CP * 8,
                                                   a_yr, a_out + 64);
@@ -87,7 +108,7 @@ void run(int warps, int batches) {
   double *sink;
   cudaMalloc(&cyc, 148 * 32 * sizeof(long long));
   cudaMalloc(&sink, 148 * 1024 * sizeof(double));
-  size_t smem = (size_t)warps * ((16 + 8) * 32 * K + (16 + 8) * 32 + 64) * 8;
+  size_t smem = (size_t)warps * ((16 + 8) * 32 * K + (16 + 8) * 32 + 64) * 8 + 96 * 1024;
   cudaFuncSetAttribute(steps_kernel<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   for (int rep = 0; rep < 2; rep++) steps_kernel<K, MODE><<<148, warps * 32, smem>>>(cyc, sink, batches, 0.7);
   cudaError_t e = cudaDeviceSynchronize();
@@ -111,6 +132,10 @@ int main() {
   run<7, 0>(1, B);
   printf("-- variants (K=5, 1 warp): 1 = no stores, 2 = no neighbour load, 4 = no coefficient adds\n");
   run<5, 1>(1, B); run<5, 2>(1, B); run<5, 3>(1, B); run<5, 4>(1, B); run<5, 5>(1, B); run<5, 6>(1, B); run<5, 7>(1, B);
+  printf("-- 16-byte stores (mode 8), K even; pair-of-rows 16-byte stores (mode 16)\n");
+  run<4, 8>(1, B); run<6, 8>(1, B); run<4, 8>(2, B); run<6, 8>(2, B); run<8, 0>(1, B); run<8, 8>(1, B);
+  printf("-- K=5: 0 = plain stores (no boundary store), 32 = weak stores, 64 = with the predicated boundary store\n");
+  run<5, 128>(1, B); run<5, 32>(1, B); run<5, 64>(1, B); run<3, 128>(1, B); run<3, 64>(1, B); run<7, 128>(1, B); run<7, 64>(1, B);
   printf("-- variants (K=1, 1 warp)\n");
   run<1, 1>(1, B); run<1, 2>(1, B); run<1, 3>(1, B); run<1, 4>(1, B); run<1, 7>(1, B);
   return 0;
