@@ -4,7 +4,7 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU library
 
-Own arm.  A "step" is one pass of the hot path over one table: S_remake(sp, a) through the C
+Own arm, N = 1.  A "step" is one pass of the hot path over one table: S_remake(sp, a) through the C
 ABI of libstb_b200.so -- the full N=200 000 x M=20 000 FP64 log S table of BASELINE config 2,
 3 799 790 001 stored cells, 30.4 GB written to HBM -- followed by a batched read-back of 100 000
 (n, m) cells from HOST buffers (stb_S_batch: H2D of the index arrays, gather kernel, D2H of the
@@ -14,13 +14,22 @@ values), which is what a caller such as samplea's aterms does with a fresh table
            recorded inside the library around the launch; nothing is host-resident for a fill:
            its only inputs are N, M and a).
   e2e    = cells / wall time of the whole step through the C ABI with host buffers.
-With --gpus N > 1 every rank owns one table of a discount sweep at the same shape (rank r fills
-discount a_r); no traffic during the fill, one final NCCL all_gather of the per-table check sums.
-"scaling" is therefore weak: per-GPU work is fixed.
+A single table does not shard (rows are sequential, every cell needs its left neighbour).
 
-Reference arm (--impl reference).  The unmodified reference library compiled from
-/root/reference (oracle/_ref/libstb_ref.so, built by oracle/build_ref.sh), one process per host
-core, each timing S_make() on a bounded sample of the same workload (see SAMPLE below).
+Own arm, N > 1 (one process per GPU, torchrun).  The sharded workload of BASELINE.json: config 3, the
+discount sweep -- 4096 discounts a_j = (j + 0.5) / 4096, a full N=50 000 x M=5 000 FP64 log S table each
+(the reference's unit: one S_remake per evaluation of samplea's log-posterior, lib/samplea.c:57-60),
+9.73e11 cells per step in all.  STRONG scaling: the 4096 tables are dealt j mod N to the ranks, no traffic
+while they are filled; per table the sum over 100 000 fixed (n, m) look-ups and the last row are kept, and
+the step ends with the one collective of the path, an NCCL all_gather of the per-table sums (32 KB) and
+last rows (164 MB in all).  value = all cells / max over ranks of the device time; e2e = all cells / wall
+time of the step including the copies of the results to the host and the gather.  The N = 1 line carries
+the same sweep on one GPU under extras.config3_sweep (all 4096 discounts), so that the sweep's scaling can be
+read against its own one-GPU rate.
+
+Reference arm (--impl reference).  The unmodified reference library compiled from /root/reference
+(oracle/_ref/libstb_ref.so, built by oracle/build_ref.sh), one process per host core, each timing S_remake()
+of a warm table on a bounded sample of the same workload (see SAMPLE below) -- the same call the GPU arm times.
 """
 from __future__ import annotations
 
@@ -44,6 +53,8 @@ BYTES_PER_CELL = 8  # FP64 table; algorithmic traffic is the store of each cell,
 # CPU sample of the same table: by the column-prefix property (the first M' columns of a table do
 # not depend on M) this IS a part of the config-2 table: its first SAMPLE_M columns, first SAMPLE_N rows.
 SAMPLE_N, SAMPLE_M = 100_000, 1_000
+# BASELINE.json configs[2]: the sweep the N > 1 runs shard; its CPU sample is the first SAMPLE_M columns of one of its tables
+N3, M3, NA3, NPAIRS3 = 50_000, 5_000, 4096, 100_000
 S_STABLE, S_NOMIRROR = 1, 1 << 17
 
 
@@ -106,28 +117,31 @@ class ClockSampler:
 # the reference CPU library on host cores
 # ------------------------------------------------------------------------------------------------
 def _ref_worker(args):
-    """One process: `reps` S_make() calls of the sample table at discount a; returns seconds each."""
+    """One process: a table of the sample shape is built once (untimed), then `reps` S_remake() calls at
+    discount a are timed -- the call the GPU arm times (lib/stable.c:549-554); returns (seconds, check) each."""
     so, kind, N, M, a, reps = args
     L = C.CDLL(so)
     out = []
     if kind == "reference":
         L.S_make.restype, L.S_make.argtypes = C.c_void_p, [C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_double, C.c_uint32]
+        L.S_remake.restype, L.S_remake.argtypes = C.c_int, [C.c_void_p, C.c_double]
         L.S_free.restype, L.S_free.argtypes = None, [C.c_void_p]
         L.S_S.restype, L.S_S.argtypes = C.c_double, [C.c_void_p, C.c_uint, C.c_uint]
+        sp = L.S_make(N, M, N, M, a * 0.9, S_STABLE)
         for _ in range(reps):
             t0 = time.perf_counter()
-            sp = L.S_make(N, M, N, M, a, S_STABLE)
+            L.S_remake(sp, a)
             dt = time.perf_counter() - t0
-            chk = L.S_S(sp, N, M)
-            L.S_free(sp)
-            out.append((dt, chk))
+            out.append((dt, L.S_S(sp, N, M)))
+        L.S_free(sp)
     else:  # the oracle's restatement of the same loop (only when the reference build did not travel)
         import numpy as np
 
         L.orc_fill_S.restype, L.orc_fill_S.argtypes = None, [C.c_uint, C.c_uint, C.c_double, C.POINTER(C.c_double), C.c_size_t]
+        tab = np.empty((N, M))
+        L.orc_fill_S(N, M, a * 0.9, tab.ctypes.data_as(C.POINTER(C.c_double)), M)  # warm: pages touched
         for _ in range(reps):
             t0 = time.perf_counter()
-            tab = np.empty((N, M))
             L.orc_fill_S(N, M, a, tab.ctypes.data_as(C.POINTER(C.c_double)), M)
             dt = time.perf_counter() - t0
             out.append((dt, float(tab[N - 1, M - 1])))
@@ -151,27 +165,29 @@ def _usable_procs(per_proc_bytes):
     return max(1, min(cores, int(avail * 0.5 // per_proc_bytes)))
 
 
-def cpu_table_rate(procs, reps):
-    """cells/s of the CPU library over `procs` concurrent processes, `reps` S_make each."""
+def cpu_table_rate(procs, reps, shape=None, a0=DISCOUNT):
+    """cells/s of the CPU library over `procs` concurrent processes, `reps` timed S_remake each (the untimed
+    S_make of every process happens inside the pool call but outside the timed intervals)."""
     import multiprocessing as mp
 
     so, kind = _cpu_library()
     if so is None:
         return None
-    cells = cells_S(SAMPLE_N, SAMPLE_M)
-    jobs = [(so, kind, SAMPLE_N, SAMPLE_M, DISCOUNT - 0.003 * i, reps) for i in range(procs)]
-    t0 = time.perf_counter()
+    N, M = shape or (SAMPLE_N, SAMPLE_M)
+    cells = cells_S(N, M)
+    jobs = [(so, kind, N, M, a0 - 0.003 * i, reps) for i in range(procs)]
     if procs == 1:
         res = [_ref_worker(jobs[0])]
     else:
         with mp.get_context("fork").Pool(procs) as pool:
             res = pool.map(_ref_worker, jobs)
-    wall = time.perf_counter() - t0
+    # the processes run side by side: the job's rate is the sum of the processes' own rates
     per_call = [dt for r in res for dt, _ in r]
-    return {"kind": kind, "cores": procs, "wall_s": wall, "cells_per_s": cells * procs * reps / wall,
-            "s_per_table": sum(per_call) / len(per_call), "check": res[0][0][1],
-            "sample": f"S_make N={SAMPLE_N} M={SAMPLE_M} a~{DISCOUNT} S_STABLE FP64 ({cells} cells: the first "
-                      f"{SAMPLE_M} columns x {SAMPLE_N} rows of the config-2 table), {reps} per process"}
+    rate = sum(cells * len(r) / sum(dt for dt, _ in r) for r in res)
+    return {"kind": kind, "cores": procs, "cells_per_s": rate, "s_per_table": sum(per_call) / len(per_call),
+            "check": res[0][0][1], "shape": [N, M],
+            "sample": f"S_remake of a warm N={N} M={M} a~{a0} S_STABLE FP64 table ({cells} cells: the first "
+                      f"{M} columns x {N} rows of the workload's table), {reps} per process"}
 
 
 def run_reference(args):
@@ -182,24 +198,31 @@ def run_reference(args):
     if so is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libstb_ref.so was not built"}))
         return 0
-    cells = cells_S(SAMPLE_N, SAMPLE_M)
+    C.CDLL(so)  # in this process too (the workers are forked children): the driver's loaded-library record sees it
+    sweep = args.gpus > 1  # the own arm's workload at N > 1 is the config-3 sweep
+    shape = (N3, SAMPLE_M) if sweep else (SAMPLE_N, SAMPLE_M)
+    a0 = 0.5 if sweep else DISCOUNT
+    cells = cells_S(*shape)
     procs = _usable_procs(per_proc_bytes=cells * 8 * 1.2)
     for _ in range(args.warmup):
-        cpu_table_rate(procs, 1)
+        cpu_table_rate(procs, 1, shape, a0)
     t0 = time.perf_counter()
-    per_step = []
+    rates, secs = [], []
     for _ in range(args.steps):
-        r = cpu_table_rate(procs, 1)
-        per_step.append(r["wall_s"])
+        r = cpu_table_rate(procs, 1, shape, a0)
+        rates.append(r["cells_per_s"])
+        secs.append(r["s_per_table"])
     wall = time.perf_counter() - t0
-    value = cells * procs * args.steps / sum(per_step)
+    value = sum(rates) / len(rates)
+    workload = (f"config 3: discount sweep, {NA3} x S_remake N={N3} M={M3} FP64 log S" if sweep else
+                f"config 2: S_remake N={N_ROWS} M={M_COLS} a={DISCOUNT} FP64 log S")
     line = {
         "impl": "reference", "metric": "log-Stirling table cells/s", "value": value, "unit": "cells/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * sum(per_step) / args.steps, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "strong" if sweep else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"config 2: S_make N={N_ROWS} M={M_COLS} a={DISCOUNT} FP64 log S; CPU arm times a "
-                               f"bounded sample of it per step: {procs} processes x one S_make N={SAMPLE_N} M={SAMPLE_M}"},
+        "config": {"workload": workload + f"; the CPU arm times a bounded sample of it per step: {procs} processes x one "
+                               f"S_remake of a warm N={shape[0]} M={shape[1]} table (its first {shape[1]} columns)"},
         "cpu_baseline": {"value": value, "unit": "cells/s", "cores": procs, "kind": kind, "sample": r["sample"]},
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": wall,
@@ -232,6 +255,17 @@ def config4_counts():
     return stb.Counts(n_rows, t_rows)
 
 
+def sweep_inputs():
+    """config 3: the 100 000 seeded (n, m) look-ups kept per table and the 4096 discounts"""
+    import numpy as np
+
+    rng = np.random.default_rng(3)
+    n = rng.integers(3, N3 + 1, size=NPAIRS3).astype(np.uint32)
+    m = np.minimum(rng.integers(2, M3 + 1, size=NPAIRS3), n - 1).astype(np.uint32)
+    a = (np.arange(NA3) + 0.5) / NA3
+    return n, m, a
+
+
 def run_extras():
     import numpy as np
 
@@ -239,24 +273,38 @@ def run_extras():
 
     L = stb.lib()
     out = {}
-    # --- config 3: discount sweep, N=50 000 M=5 000, a_j = (j+0.5)/4096; a 96-discount slice of the 4096 ---
-    N3, M3, na = 50_000, 5_000, 96
-    rng = np.random.default_rng(3)
-    n = rng.integers(3, N3 + 1, size=100_000).astype(np.uint32)
-    m = np.minimum(rng.integers(2, M3 + 1, size=100_000), n - 1).astype(np.uint32)
+    # --- config 3: the discount sweep on ONE GPU, all 4096 discounts (the N > 1 runs shard exactly this) ---
+    n, m, a = sweep_inputs()
     w = stb.Sweep(N3, M3)
     w.set_pairs(n, m)
-    a = (np.arange(0, 4096, 4096 // na)[:na] + 0.5) / 4096
     w.run(a[:12], gather=False, sums=True)  # warm-up
     t0 = time.perf_counter()
-    _, sums, _ = w.run(a, gather=False, sums=True)
+    _, sums, last = w.run(a, gather=False, sums=True, lastrow=True)
     wall = time.perf_counter() - t0
-    cells = cells_S(N3, M3) * na
-    out["config3_sweep"] = {"discounts": na, "of": 4096, "tables_per_launch": w.tables_in_flight,
+    cells = cells_S(N3, M3) * NA3
+    T = w.tables_in_flight
+    waves = -(-NA3 // T)
+    out["config3_sweep"] = {"discounts": NA3, "of": NA3, "tables_per_launch": T, "waves": waves,
+                            "wave_quantisation": NA3 / (waves * T),
                             "cells_per_s_device": cells / (w.last_fill_ms * 1e-3), "cells_per_s_e2e": cells / wall,
+                            "device_ms": w.last_fill_ms, "wall_s": wall,
                             "hbm_frac": cells * 8 / (w.last_fill_ms * 1e-3) / 1e9 / 6544.7,
-                            "finite": bool(np.isfinite(sums).all())}
+                            "kept_per_table": "sum over 100 000 (n,m) look-ups + last row (5 000 values), copied to the host",
+                            "finite": bool(np.isfinite(sums).all() and np.isfinite(last).all())}
     w.free()
+    # --- the GPU arm at the CPU arm's sample shape (so that the two arms can be compared on the same table) ---
+    ts = stb.Table(SAMPLE_N, SAMPLE_M, SAMPLE_N, SAMPLE_M, DISCOUNT * 0.9, stb.S_STABLE | stb.S_NOMIRROR)
+    ms, t0 = [], time.perf_counter()
+    for _ in range(5):
+        ts.remake(DISCOUNT)
+        ms.append(ts.last_fill_ms)
+    wall = (time.perf_counter() - t0) / 5
+    out["cpu_sample_shape_on_gpu"] = {"shape": [SAMPLE_N, SAMPLE_M], "cells": cells_S(SAMPLE_N, SAMPLE_M),
+                                      "kernel_ms": min(ms), "cells_per_s_device": cells_S(SAMPLE_N, SAMPLE_M) / (min(ms) * 1e-3),
+                                      "cells_per_s_e2e": cells_S(SAMPLE_N, SAMPLE_M) / wall,
+                                      "note": "S_remake of the N=100 000 x M=1 000 table the reference arm times per process: 1 000 "
+                                              "columns keep 7 of 148 SMs busy, the rate of the full table is the headline"}
+    ts.free()
     # --- config 4: batched samplea + sampleb, 100 000 nodes, C chains, loops=1 ---
     cts = config4_counts()
     Cn = 1024
@@ -305,7 +353,37 @@ def run_extras():
         _extras_samplea2(out, stb, cts, bpar)
     except Exception as exc:
         out["config4_samplea2"] = {"error": repr(exc)}
+    try:
+        _extras_dropin_default(out)
+    except Exception as exc:
+        out["config1_dropin_default_flags"] = {"error": repr(exc)}
     return out
+
+
+def _extras_dropin_default(out):
+    """config 1 the way an unmodified libstb caller runs it (default flags: host mirror on): S_make, 20 x S_remake each
+    followed by a look-up, then 1e7 scalar S_V calls -- oracle/bench_dropin.c compiled against this library and against
+    the reference (oracle/build_ref.sh), each run as its own process"""
+    res = {}
+    for name, exe in (("b200", "dropin_bench_b200"), ("reference", "dropin_bench_ref")):
+        path = os.path.join(ROOT, "oracle", "_ref", exe)
+        if not os.path.exists(path):
+            continue
+        if name == "b200":
+            subprocess.run([path, "2000", "200", "1", "1000"], capture_output=True, text=True, timeout=300)  # CUDA context / first-touch warm-up is per process: shown by make_s
+        r = subprocess.run([path, "10000", "1000", "20", "10000000"], capture_output=True, text=True, timeout=600)
+        if r.returncode != 0:
+            res[name] = {"error": (r.stderr or "")[-300:]}
+            continue
+        res[name] = json.loads(r.stdout.strip().splitlines()[-1])
+    if "b200" in res and "reference" in res and "error" not in res["b200"] and "error" not in res["reference"]:
+        b, rf = res["b200"], res["reference"]
+        res["speedup_remake"] = rf["remake_s_each"] / b["remake_s_each"]
+        res["lookup_ns_ratio"] = b["lookup_ns_each"] / rf["lookup_ns_each"]
+        res["total_s"] = {k: v["make_s"] + v["remakes"] * v["remake_s_each"] + v["lookup_s"] for k, v in (("b200", b), ("reference", rf))}
+    res["what"] = ("S_make(10000,1000,10000,1000,0.5,S_STABLE|S_UVTABLE); 20 x (S_remake + one S_V); 1e7 scalar S_V at random (n,m); "
+                   "default flags: the host mirror serves the scalar calls (pinned 4 MB row blocks fetched on first touch, kept across refills)")
+    out["config1_dropin_default_flags"] = res
 
 
 def _extras_samplea2(out, stb, cts, bpar):
@@ -427,30 +505,14 @@ def run_own(args):
 
     import libstb_b200 as stb
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world, rank, local = 1, 0, int(os.environ.get("LOCAL_RANK", "0"))  # one table, one GPU (N > 1: run_own_sweep)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU library)")
     torch.cuda.set_device(local)
-    dist = None
-    saved_stdout = None
-    if world > 1:
-        import torch.distributed as dist
-
-        # stdout carries ONE JSON line: whatever libraries print there meanwhile (NCCL's version
-        # banner) goes to stderr
-        sys.stdout.flush()
-        saved_stdout = os.dup(1)
-        os.dup2(2, 1)
-
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = stb.lib()
     N, M = args.rows, args.cols
     cells = cells_S(N, M)
-    a_rank = DISCOUNT - 0.05 * rank  # rank r owns discount a_r of the sweep; rank 0 is config 2 itself
+    a_rank = DISCOUNT
 
     # pinned host buffers of the per-step read-back
     rng = np.random.default_rng(2024 + rank)
@@ -476,8 +538,6 @@ def run_own(args):
         return ms
 
     def barrier():
-        if dist is not None:
-            dist.barrier()
         torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3) if not args.allow_short_warmup else args.warmup):
@@ -489,21 +549,12 @@ def run_own(args):
     t0 = time.time()
     w0 = time.perf_counter()
     fill_ms = [step() for _ in range(args.steps)]
-    checksum = float(out_h.numpy().sum())  # the values are already on the host (stb_S_batch copies them back)
-    if dist is not None:  # the sweep's one collective: gather the per-table results
-        mine = torch.tensor([a_rank, checksum], dtype=torch.float64, device="cuda")
-        allv = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(allv, mine)
     barrier()
     wall = time.perf_counter() - w0
     t1 = time.time()
     clocks = sampler.stop(t0, t1) if rank == 0 else None
 
     dev_s = sum(fill_ms) / 1e3
-    if dist is not None:
-        tt = torch.tensor([dev_s, wall], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dev_s, wall = float(tt[0]), float(tt[1])
 
     # parity spot-check of what was just computed (size-independent properties; tests/ hold the rest)
     ok = bool(np.isfinite(out_h.numpy()).all())
@@ -537,8 +588,9 @@ def run_own(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": f"config 2: S_remake of the N={N} M={M} a={DISCOUNT} FP64 log S table ({cells} cells, "
-                            f"{cells * 8 / 1e9:.1f} GB) + stb_S_batch read-back of {N_LOOKUP} cells per step; with "
-                            f"N GPUs each rank fills its own discount of a sweep at this shape",
+                            f"{cells * 8 / 1e9:.1f} GB) + stb_S_batch read-back of {N_LOOKUP} cells per step (a single table "
+                            f"does not shard; with --gpus N > 1 the step is the config-3 discount sweep, see extras.config3_sweep "
+                            f"for the same sweep on this one GPU)",
                 "l2": "each step rewrites the whole table (>> 126 MB L2); no input is re-read",
                 "timing": "value: CUDA events around the fill kernel on its launch stream, summed over steps, max over "
                           "ranks; e2e: wall clock of the C-ABI calls with pinned host buffers",
@@ -567,19 +619,217 @@ def run_own(args):
             line["extras"] = run_extras()
         except Exception as exc:  # the extras never take the headline line down
             line["extras"] = {"error": repr(exc)}
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
-    if saved_stdout is not None:
-        sys.stdout.flush()
-        os.dup2(saved_stdout, 1)
-        os.close(saved_stdout)
     if rank == 0:
         print(json.dumps(line))
         if not ok:
             print("bench.py: parity spot check FAILED", file=sys.stderr)
             return 1
     return 0
+
+
+def run_own_sweep(args):
+    """N > 1: the config-3 discount sweep, strong-scaled over the ranks (one process per GPU)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import libstb_b200 as stb
+    from libstb_b200 import shard
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU library)")
+    torch.cuda.set_device(local)
+    # stdout carries ONE JSON line: whatever libraries print there meanwhile (NCCL's banner) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = stb.lib()
+    na = args.discounts
+    n, m, a_all = sweep_inputs()
+    a_all = (np.arange(na) + 0.5) / na
+    mine = shard.my_units(na, rank, world)  # table j on rank j mod world
+    cells_tab = cells_S(N3, M3)
+    w = stb.Sweep(N3, M3)
+    w.set_pairs(n, m)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    dev = torch.device("cuda", local)
+    per = (na + world - 1) // world
+    # results of a step on the device for the gather: [per][1 + M3] = sum, last row (padded shares stay NaN)
+    send = torch.full((per, 1 + M3), float("nan"), dtype=torch.float64, device=dev)
+    recv = torch.empty((world, per, 1 + M3), dtype=torch.float64, device=dev)
+    host = torch.empty((mine.shape[0], 1 + M3), dtype=torch.float64).pin_memory()
+
+    def step():
+        # the C-ABI call with HOST result buffers (sums and last rows come back over PCIe), then the collective
+        _, sums, last = w.run(a_all[mine], gather=False, sums=True, lastrow=True)
+        ms = w.last_fill_ms
+        hn = host.numpy()
+        hn[:, 0] = sums
+        hn[:, 1:] = last
+        send[: mine.shape[0]].copy_(host, non_blocking=True)
+        dist.all_gather_into_tensor(recv, send)
+        return ms
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3) if not args.allow_short_warmup else args.warmup):
+        step()
+    if rank == 0:
+        sampler.wait_first()
+    barrier()
+    t0 = time.time()
+    w0 = time.perf_counter()
+    fill_ms = [step() for _ in range(args.steps)]
+    barrier()
+    wall = time.perf_counter() - w0
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    tt = torch.tensor([sum(fill_ms) / 1e3, wall], dtype=torch.float64, device=dev)
+    each = [torch.empty_like(tt) for _ in range(world)]
+    dist.all_gather(each, tt)
+    dev_each = [float(x[0]) for x in each]
+    dev_s, wall = max(dev_each), max(float(x[1]) for x in each)
+
+    # parity of the gathered results: every rank's tables against this rank's own refill of a few of them, bit for bit
+    allres = recv.cpu().numpy()
+    ok = True
+    if rank == 0:
+        rng = np.random.default_rng(11)
+        probe = np.unique(np.concatenate([rng.integers(0, na, size=6), [0, na - 1, min(na - 1, world)]]))
+        _, s_chk, l_chk = w.run(a_all[probe], gather=False, sums=True, lastrow=True)
+        for k, j in enumerate(probe):
+            r, pos = int(j % world), int(j // world)
+            ok = ok and allres[r, pos, 0] == s_chk[k] and np.array_equal(allres[r, pos, 1:], l_chk[k])
+        full = np.stack([allres[j % world, j // world] for j in range(na)])
+        ok = ok and bool(np.isfinite(full).all())
+    # the same sweep through the single-process multi-device entry of the C ABI (rank 0 drives every GPU)
+    cabi = None
+    barrier()
+    if rank == 0 and not args.no_extras:
+        try:
+            mw = stb.SweepMulti(N3, M3, list(range(world)))
+            mw.set_pairs(n, m)
+            mw.run(a_all[: 4 * world], gather=False, sums=True)  # warm-up
+            c0 = time.perf_counter()
+            _, s_m, l_m = mw.run(a_all, gather=False, sums=True, lastrow=True)
+            c_wall = time.perf_counter() - c0
+            same = all(s_m[j] == allres[j % world, j // world, 0] for j in range(na))
+            cabi = {"entry": "stb_sweep_multi_run (one process, one host thread per device)", "devices": world,
+                    "cells_per_s_device": cells_tab * na / (mw.last_fill_ms * 1e-3), "cells_per_s_e2e": cells_tab * na / c_wall,
+                    "device_ms_each": mw.device_ms, "equals_per_rank_results_bit_for_bit": bool(same)}
+            ok = ok and same
+            mw.free()
+        except Exception as exc:
+            cabi = {"error": repr(exc)}
+    chains = None
+    if not args.no_extras:
+        try:
+            chains = _sharded_chains(stb, dist, rank, world, dev)
+        except Exception as exc:
+            chains = {"error": repr(exc)}
+    barrier()
+    line = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        # a kernel timed inside a long step: the sustained figure when the driver wrote one
+        peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks \
+            else (6650.0, "fallback (B200_PROFILING.md)")
+        T = w.tables_in_flight
+        waves = -(-mine.shape[0] // T)
+        ms_step = 1e3 * dev_s / args.steps
+        achieved = cells_tab * mine.shape[0] * 8 / (sum(fill_ms) / len(fill_ms) * 1e-3) / 1e9  # this rank's kernel
+        line = {
+            "metric": "log-Stirling table cells/s", "value": cells_tab * na * args.steps / dev_s, "unit": "cells/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"config 3: discount sweep, {na} discounts a_j=(j+0.5)/{na}, one N={N3} M={M3} FP64 log S table each "
+                            f"({cells_tab * na:.3e} cells, {cells_tab * na * 8 / 1e12:.2f} TB written per step), table j on rank j mod {world}; "
+                            f"kept per table: the sum over {NPAIRS3} (n,m) look-ups and the last row, all_gather (NCCL) of both at the "
+                            f"end of the step; no traffic between GPUs during the fills",
+                "l2": "every wave of tables (6 x 1.9 GB per GPU) overwrites the slabs of the previous one (>> 126 MB L2)",
+                "timing": "value: CUDA events around each rank's queue of fills and reductions, summed over steps, max over "
+                          "ranks; e2e: wall clock of the whole step (C-ABI call with host result buffers + gather), max over ranks",
+                "wave_quantisation": {"tables_per_launch": T, "waves_per_rank": waves,
+                                      "efficiency": mine.shape[0] / (waves * T)},
+                "device_s_each_rank": dev_each,
+                "parity_spot_check": bool(ok),
+            },
+            "e2e": {"value": cells_tab * na * args.steps / wall, "unit": "cells/s", "h2d_bytes_per_step": 8 * mine.shape[0] * world,
+                    "d2h_bytes_per_step": 8 * (1 + M3) * na, "ms_per_step": 1e3 * wall / args.steps},
+            "gpu_launches": args.steps * waves * 3 * world,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "stb::fill_strip_kernel (per GPU, rank 0's launches)",
+                         "kernel_ms": sum(fill_ms) / len(fill_ms) / waves},
+            "clocks": clocks,
+            "extras": {"c_abi_multi_device": cabi, "config4_chains_sharded": chains},
+        }
+    w.free()
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
+    if rank == 0:
+        print(json.dumps(line))
+        if not ok:
+            print("bench.py: parity spot check FAILED", file=sys.stderr)
+            return 1
+    return 0
+
+
+def _sharded_chains(stb, dist, rank, world, dev):
+    """config 4 over the ranks: 4096 chains of samplea + sampleb, chain c on rank c mod world, one all_gather of the draws"""
+    import numpy as np
+    import torch
+
+    from libstb_b200 import shard
+
+    L = stb.lib()
+    cts = config4_counts()
+    Cn = 4096
+    mine = shard.my_units(Cn, rank, world)
+    bpar = np.full(cts.I, 10.0)
+    a0 = (0.05 + 0.9 * (np.arange(Cn) + 0.5) / Cn)[mine]
+    r0 = np.array([L.stb_rng48_state(12345 + int(c)) for c in mine], dtype=np.uint64)
+    aw, rw, _ = stb.samplea_batch(a0[:64], cts, bpar, r0[:64], loops=1)  # warm-up (contexts are kept between calls)
+    stb.sampleb_batch(np.full(64, 10.0), cts, 1.1, 20.0, aw, rw, loops=1)
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    a1, r1, sa = stb.samplea_batch(a0, cts, bpar, r0, loops=1)
+    b1, _, sb = stb.sampleb_batch(np.full(mine.shape[0], 10.0), cts, 1.1, 20.0, a1, r1, loops=1)
+    draws = shard.gather_units(np.stack([a1, b1], axis=1), Cn, rank, world, dist, dev)
+    torch.cuda.synchronize()
+    wall = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+    # chain 0..world-1 again on this rank alone: a chain's draw does not depend on where it ran
+    same = True
+    if rank == 0:
+        k = np.arange(min(world, 8))
+        ra = np.array([L.stb_rng48_state(12345 + int(c)) for c in k], dtype=np.uint64)
+        a2, r2, _ = stb.samplea_batch(0.05 + 0.9 * (k + 0.5) / Cn, cts, bpar, ra, loops=1)
+        b2, _, _ = stb.sampleb_batch(np.full(k.shape[0], 10.0), cts, 1.1, 20.0, a2, r2, loops=1)
+        same = bool(np.array_equal(draws[k, 0], a2) and np.array_equal(draws[k, 1], b2))
+    a_all, b_all = draws[:, 0], draws[:, 1]
+    return {"chains": Cn, "ranks": world, "nodes": int(cts.K.sum()), "samples_per_s": 2 * Cn / float(wall[0]),
+            "wall_s": float(wall[0]), "a_device_ms_rank0": sa["eval_ms"], "a_evals_rank0": int(sa["evals"]),
+            "in_bounds": bool(((a_all >= 0.01) & (a_all <= 0.98) & (b_all >= 0.01) & (b_all <= 2000)).all()),
+            "draws_independent_of_rank": same}
 
 
 def main():
@@ -590,12 +840,15 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--rows", type=int, default=N_ROWS, help="development only; the judged run uses the default")
     ap.add_argument("--cols", type=int, default=M_COLS, help="development only; the judged run uses the default")
+    ap.add_argument("--discounts", type=int, default=NA3, help="development only (N > 1): tables of the sweep; the judged run uses 4096")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the config 3 / config 4 side measurements")
     ap.add_argument("--allow-short-warmup", action="store_true", help="profiling runs only")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        return run_own_sweep(args)
     return run_own(args)
 
 

@@ -62,11 +62,15 @@ for p in demo check; do
   $CC -O2 -w -I"$REF/lib" "$REF/test/$p.c" -o "$OUT/ref_$p" "$OUT/libstb_ref.so" -Wl,-rpath,'$ORIGIN' -lm
 done
 $CC -O2 -fPIC -shared -o "$OUT/shim_time.so" "$HERE/shim_time.c"
+#   oracle/_ref/dropin_bench_{ref,b200}   oracle/bench_dropin.c (the default-flags caller pattern, timed) against either library
+$CC -O2 -w -I"$REF/lib" "$HERE/bench_dropin.c" -o "$OUT/dropin_bench_ref" "$OUT/libstb_ref.so" -Wl,-rpath,'$ORIGIN' -lm
 LIBDIR="$HERE/../libstb_b200/lib"
 if [ -f "$LIBDIR/libstb_b200.so" ]; then
   for p in list demo check; do
     $CC -O2 -w -I"$HERE/../include" "$REF/test/$p.c" -o "$OUT/dropin_$p" -L"$LIBDIR" -lstb_b200 \
         -Wl,-rpath,'$ORIGIN/../../libstb_b200/lib' -lm
   done
-  echo "built $OUT/ref_list and $OUT/dropin_{list,demo,check}"
+  $CC -O2 -w -I"$HERE/../include" "$HERE/bench_dropin.c" -o "$OUT/dropin_bench_b200" -L"$LIBDIR" -lstb_b200 \
+      -Wl,-rpath,'$ORIGIN/../../libstb_b200/lib' -lm
+  echo "built $OUT/ref_list and $OUT/dropin_{list,demo,check} and $OUT/dropin_bench_{ref,b200}"
 fi
