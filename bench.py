@@ -715,6 +715,11 @@ def run_own_sweep(args):
     # the same sweep through the single-process multi-device entry of the C ABI (rank 0 drives every GPU)
     cabi = None
     barrier()
+    # the other ranks wait on the HOST (the job's TCP store), not in an NCCL barrier: a collective's kernel spinning on
+    # their GPUs would share them with rank 0's launches
+    store = dist.distributed_c10d._get_default_store()
+    if rank != 0 and not args.no_extras:
+        store.wait(["stb_cabi_done"])
     if rank == 0 and not args.no_extras:
         try:
             mw = stb.SweepMulti(N3, M3, list(range(world)))
@@ -731,6 +736,7 @@ def run_own_sweep(args):
             mw.free()
         except Exception as exc:
             cabi = {"error": repr(exc)}
+        store.set("stb_cabi_done", "1")
     chains = None
     if not args.no_extras:
         try:

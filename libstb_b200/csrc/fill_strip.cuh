@@ -79,7 +79,9 @@ struct StripTable {  // one table of a launch
 };
 
 struct StripParams {
-  const StripTable *tables;  // device array, one per table in the launch
+  const StripTable *tables;  // device array, one per table of the launch
+  int ntables;               // tables of the launch; CTA group q (ctas CTAs) fills tables q, q + ngroups, q + 2 ngroups, ...
+  int ngroups;               // CTA groups of the launch (= tables filled side by side)
   unsigned long long ld;     // elements per table row
   int N, M;
   int C;     // columns per strip (= L*K)
@@ -121,6 +123,8 @@ struct StripCfg {
   static constexpr int NB = NB_FIT > 16 ? 16 : NB_FIT;
   static constexpr int RS = NB * ST_RB;  // ring rows; rows RS..RS+7 duplicate rows 0..7
   static_assert(NB >= 6, "x ring too small for this geometry");
+  // one strip per CTA and a deep ring: the flusher reads the boundary column from the x ring (strip_producer)
+  static constexpr bool FLUSH_FROM_XRING = (G == 1) && (NB >= 16);
 };
 
 // ---- shared memory -----------------------------------------------------------------------------
@@ -323,7 +327,7 @@ __device__ __forceinline__ void sts_s32_if(unsigned a, int v, bool pred) {
  * rescale), a product of two powers of two, converts them exactly.  Everything is stored unconditionally: rows that do not exist (before the
  * strip's first row, past N) land in ring slots the consumers never read as valid.
  */
-template <int K, bool HAS_V, bool DUP, int CP, int RS, bool FIRST>
+template <int K, bool HAS_V, bool DUP, int CP, int RS, bool FIRST, bool OUT>
 __device__ __forceinline__ void strip_steps(double (&x)[K], const double (&ma)[K], double &nm1, double &yin,
                                             const unsigned first_addr, const double scn0, const double scn,
                                             unsigned &nb_addr,
@@ -361,7 +365,7 @@ __device__ __forceinline__ void strip_steps(double (&x)[K], const double (&ma)[K
     nm1 += 1.0;
     sts_f64(xr + (i * CP + K - 1) * 8, x[K - 1]);
     if (DUP) sts_f64(xr + ((RS + i) * CP + K - 1) * 8, x[K - 1]);
-    sts_f64_if(outp + i * 8, x[K - 1], write_out);
+    if (OUT) sts_f64_if(outp + i * 8, x[K - 1], write_out);  // (G == 1: the flusher takes the column from the x ring)
     yin = nb * ((FIRST && i == 0) ? scn0 : scn);
   }
   // the last row's remaining columns
@@ -425,6 +429,15 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
   const bool lane0 = (lane == 0);
   const bool take_bnd = lane0 && has_left;  // lane 0 of the first strip reads zeros times zero
   const bool write_out = has_right && (lane == L - 1);
+  // The strip's last column goes to the right-hand neighbour.  Inside a CTA (G > 1) the producer stores it a
+  // second time, into the neighbour's boundary ring.  With one strip per CTA (the shapes the planner picks)
+  // nobody in the CTA reads that ring: the flusher takes the column straight from the x ring -- it is one more
+  // reader of the ring slots, its progress word (rout->taken) is what the producer's flow control looks at --
+  // and the recurrence's step is one predicated store shorter.
+  // (only when the x ring is deep enough: the flusher then has NB/2 = 8 batches to follow the producer in, as many
+  // as it needs not to hold it back; K = 7 strips have 12 slots and keep the boundary ring -- measured on the
+  // config-3 shape: 5 % slower without it)
+  constexpr bool OUT = !StripCfg<K, G, HAS_V>::FLUSH_FROM_XRING;
   // shared addresses, formed once
   const unsigned a_xr = smem_u32(&sb.xring[lane * K]);
   const unsigned a_yr = smem_u32(&sb.yring[HAS_V ? lane : 0]);
@@ -470,7 +483,9 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
     // of each slot are finished
     int jb = p + g.delta;
     if (jb > jlast) jb = jlast;
-    const int need_in = has_left ? jb : NO_NEED, need_out = has_right ? p - ST_NBR : NO_NEED;
+    // batch p overwrites the x-ring rows of batch p - NB/2: the flusher must be done with that one (G == 1);
+    // G > 1: the boundary ring holds ST_NBR batches
+    const int need_in = has_left ? jb : NO_NEED, need_out = has_right ? p - (OUT ? ST_NBR : NB / 2) : NO_NEED;
     if (gen_next.x < gen_need || gen_next.y < gen_need || c_in < need_in || c_out < need_out) {
       if (!producer_wait(a_gen + s0 * 4, gen_need, a_in_written, need_in, a_out_taken, need_out, P.abort_flag)) return;
       c_in = max(c_in, need_in);
@@ -488,7 +503,7 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
     if (lane0) sE = has_left ? lds_s32(a_in_e + bs * 4) : elow;
     // (lane 0 of a table's first strip has no left neighbour: what it reads is multiplied by 0)
     const double scn = (lane0 && !has_left) ? 0.0 : pow2i(sE - elow);
-    sts_s32_if(a_out_e + os * 4, elow, write_out);
+    if (OUT) sts_s32_if(a_out_e + os * 4, elow, write_out);
     const unsigned bnd = a_in_x + bs * (ST_B * 8);
     const unsigned outp = a_out_x + os * (ST_B * 8);
     const unsigned xr = a_xr + s0 * (ST_RB * CP * 8);
@@ -502,10 +517,10 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
     ST_TICK(tk3);
     // ---- sixteen steps, eight per consumer slot; only ring rows 0..7 have duplicates ----
     if (s0 == 0)
-      strip_steps<K, HAS_V, true, CP, RS, true>(x, ma, nm1, yin, first_addr, scn0, scn, nb_addr, nb_stride, write_out, xr,
+      strip_steps<K, HAS_V, true, CP, RS, true, OUT>(x, ma, nm1, yin, first_addr, scn0, scn, nb_addr, nb_stride, write_out, xr,
                                                 yr, outp);
     else
-      strip_steps<K, HAS_V, false, CP, RS, true>(x, ma, nm1, yin, first_addr, scn0, scn, nb_addr, nb_stride, write_out,
+      strip_steps<K, HAS_V, false, CP, RS, true, OUT>(x, ma, nm1, yin, first_addr, scn0, scn, nb_addr, nb_stride, write_out,
                                                  xr, yr, outp);
     // mid-batch: fetch the words the NEXT batch's flow control will look at, fix the next scale
     {
@@ -523,7 +538,7 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
       asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a_er + (((p + 1) & (ST_NJ - 1)) * 32) * 4),
                    "r"((unsigned)elow_n + (0x80000000u - 1023u)));
     }
-    strip_steps<K, HAS_V, false, CP, RS, false>(x, ma, nm1, yin, 0u, scn, scn, nb_addr, nb_stride, write_out,
+    strip_steps<K, HAS_V, false, CP, RS, false, OUT>(x, ma, nm1, yin, 0u, scn, scn, nb_addr, nb_stride, write_out,
                                                 xr + ST_RB * CP * 8, yr + (HAS_V ? ST_RB * 32 * 8 : 0),
                                                 outp + ST_RB * 8);
     ST_TICK(tk4);
@@ -533,7 +548,7 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
     release_cta();
     sts_s32_if(a_prog, p, lane0);
     sts_s32_if(a_in_taken, p + g.delta, take_bnd);
-    sts_s32_if(a_out_written, p, write_out);
+    if (OUT) sts_s32_if(a_out_written, p, write_out);
     s0 += 2;
     if (s0 >= NB) {
       s0 = 0;
@@ -737,7 +752,14 @@ struct GBound {
   int *taken;
 };
 
-__device__ void strip_loader(const StripParams &P, BRing *ring, int delta, int lane, const GBound gb, int jlast) {
+/*
+ * A launch may fill several tables per CTA group, one after the other (the rounds of a sweep).  The global
+ * ring of a boundary is then ONE stream over the rounds: batch j of round r travels as entry J = jbase + j,
+ * jbase = r * (batches of the writing strip), in slot J mod ST_NBG with flag J + 1, and the reader's progress
+ * word counts in J as well -- nothing is reset between rounds, and the writer of round r + 1 may start as soon
+ * as the ring has room, while the reader is still finishing round r.
+ */
+__device__ void strip_loader(const StripParams &P, BRing *ring, int delta, int lane, const GBound gb, int jlast, int jbase) {
   // the boundary is written by the CTA to the left (or by the previous pass); batches delta .. jlast are needed here
   const uint4 *g = gb.g;
   constexpr int NP = 4;  // batches polled per pass (loads in flight per lane)
@@ -753,13 +775,13 @@ __device__ void strip_loader(const StripParams &P, BRing *ring, int delta, int l
     for (int u = 0; u < NP; u++) {
       const int j = next + u;
       v[u] = make_uint4(0, 0, 0, 0);
-      if (j <= lim && lane < ST_GE) v[u] = ld_volatile_v4(&g[(size_t)((unsigned)j & gb.mask) * ST_GE + lane]);
+      if (j <= lim && lane < ST_GE) v[u] = ld_volatile_v4(&g[(size_t)((unsigned)(jbase + j) & gb.mask) * ST_GE + lane]);
     }
     int got = 0;
 #pragma unroll
     for (int u = 0; u < NP; u++) {
       const int j = next + u;
-      const unsigned seq = (unsigned)(j + 1);
+      const unsigned seq = (unsigned)(jbase + j + 1);
       const bool ok = (j <= lim) && (lane >= ST_GE || (v[u].y == seq && v[u].w == seq));
       if (got == u && __all_sync(0xffffffffu, ok)) {
         if (lane < ST_B)
@@ -775,7 +797,7 @@ __device__ void strip_loader(const StripParams &P, BRing *ring, int delta, int l
       const int hi = next + got - 1;
       if (lane == 0) {
         st_vol(&ring->written, hi);
-        if (gb.taken && (hi - pub >= ST_NBG / 4 || hi == jlast)) st_release_gpu(gb.taken, hi);  // back-pressure: the entries were read
+        if (gb.taken && (hi - pub >= ST_NBG / 4 || hi == jlast)) st_release_gpu(gb.taken, jbase + hi);  // back-pressure: the entries were read
       }
       if (hi - pub >= ST_NBG / 4) pub = hi;
       next = hi + 1;
@@ -793,22 +815,59 @@ __device__ void strip_loader(const StripParams &P, BRing *ring, int delta, int l
   }
 }
 
-__device__ void strip_flusher(const StripParams &P, BRing *ring, int last, int lane, const GBound gb) {
+/*
+ * One strip per CTA: the boundary column of batch j is in the x ring, where the producer's last lane put it
+ * for the consumers -- step j*16 + i sits in ring row (2j % NB)*8 + i, column (L-1)*K + K-1 -- and the batch's
+ * exponent in the exponent ring (lane L-1).  The flusher follows the producer's progress word and is a reader
+ * of the ring slots like the consumers: its own progress (ring->taken) holds the producer back.
+ */
+template <int K, int G, bool HAS_V>
+__device__ void strip_flusher_xring(const StripParams &P, StripSub<K, G, HAS_V> &sb, BRing *ring, int last, int lane,
+                                    const GBound gb, int jbase) {
+  using Cfg = StripCfg<K, G, HAS_V>;
   uint4 *g = gb.g;
-  int c_w = -1, c_t = gb.taken ? -1 : 0x3fffffff;  // the carry buffer holds every batch: nothing to wait for
+  const unsigned a_col = smem_u32(&sb.xring[(P.L - 1) * K + K - 1]);
+  int c_w = -1, c_t = gb.taken ? -0x40000000 : 0x3fffffff;  // the reader's progress counts over the rounds (see strip_loader); unknown yet
   for (int next = 0; next <= last;) {
-    if (!ctr_wait<false, ST_HELPER_SLEEP>(&ring->written, next, P.abort_flag, c_w)) return;
-    if (gb.taken && !ctr_wait<true, 64>(gb.taken, next - ST_NBG, P.abort_flag, c_t)) return;
+    if (!ctr_wait<false, ST_HELPER_SLEEP>(&sb.progress, next, P.abort_flag, c_w)) return;
+    if (gb.taken && !ctr_wait<true, 64>(gb.taken, jbase + next - ST_NBG, P.abort_flag, c_t)) return;
     int hi = c_w < last ? c_w : last;
-    if (gb.taken && hi > c_t + ST_NBG) hi = c_t + ST_NBG;
+    if (gb.taken && hi > c_t - jbase + ST_NBG) hi = c_t - jbase + ST_NBG;
     for (int j = next; j <= hi; j++) {
-      const unsigned seq = (unsigned)(j + 1);
+      const unsigned seq = (unsigned)(jbase + j + 1);
       if (lane < ST_B) {
-        const double x = ring->x[(j & (ST_NBR - 1)) * ST_B + lane];
-        st_volatile_v4(&g[(size_t)((unsigned)j & gb.mask) * ST_GE + lane],
+        const double x = lds_f64(a_col + (unsigned)((((2 * j) % Cfg::NB) * ST_RB + lane) * Cfg::CP * 8));
+        st_volatile_v4(&g[(size_t)((unsigned)(jbase + j) & gb.mask) * ST_GE + lane],
                        make_uint4((unsigned)__double2loint(x), seq, (unsigned)__double2hiint(x), seq));
       } else if (lane == ST_B) {
-        st_volatile_v4(&g[(size_t)((unsigned)j & gb.mask) * ST_GE + lane],
+        const unsigned kb = *(volatile unsigned *)&sb.ering[(j & (ST_NJ - 1)) * 32 + (P.L - 1)];
+        st_volatile_v4(&g[(size_t)((unsigned)(jbase + j) & gb.mask) * ST_GE + lane],
+                       make_uint4(kb - (0x80000000u - 1023u), seq, 0u, seq));
+      }
+    }
+    __syncwarp();
+    release_cta();
+    if (lane == 0) st_vol(&ring->taken, hi);
+    next = hi + 1;
+  }
+}
+
+__device__ void strip_flusher(const StripParams &P, BRing *ring, int last, int lane, const GBound gb, int jbase) {
+  uint4 *g = gb.g;
+  int c_w = -1, c_t = gb.taken ? -0x40000000 : 0x3fffffff;  // the carry buffer holds every batch: nothing to wait for
+  for (int next = 0; next <= last;) {
+    if (!ctr_wait<false, ST_HELPER_SLEEP>(&ring->written, next, P.abort_flag, c_w)) return;
+    if (gb.taken && !ctr_wait<true, 64>(gb.taken, jbase + next - ST_NBG, P.abort_flag, c_t)) return;
+    int hi = c_w < last ? c_w : last;
+    if (gb.taken && hi > c_t - jbase + ST_NBG) hi = c_t - jbase + ST_NBG;
+    for (int j = next; j <= hi; j++) {
+      const unsigned seq = (unsigned)(jbase + j + 1);
+      if (lane < ST_B) {
+        const double x = ring->x[(j & (ST_NBR - 1)) * ST_B + lane];
+        st_volatile_v4(&g[(size_t)((unsigned)(jbase + j) & gb.mask) * ST_GE + lane],
+                       make_uint4((unsigned)__double2loint(x), seq, (unsigned)__double2hiint(x), seq));
+      } else if (lane == ST_B) {
+        st_volatile_v4(&g[(size_t)((unsigned)(jbase + j) & gb.mask) * ST_GE + lane],
                        make_uint4((unsigned)ring->e[j & (ST_NBR - 1)], seq, 0u, seq));
       }
     }
@@ -820,21 +879,10 @@ __device__ void strip_flusher(const StripParams &P, BRing *ring, int last, int l
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------------
-template <int K, int G, bool HAS_S, bool HAS_V, typename OutT>
-__global__ void __launch_bounds__(ST_WARPS * 32, 1) fill_strip_kernel(const StripParams P) {
-  using SM = StripSmem<K, G, HAS_V>;
+/* shared state of a CTA before it starts a table (the logarithm table is loaded once per launch) */
+template <int K, int G, bool HAS_V>
+__device__ __forceinline__ void cta_reset(StripSmem<K, G, HAS_V> &sm, const StripParams &P, int strip0) {
   using Cfg = StripCfg<K, G, HAS_V>;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  SM &sm = *reinterpret_cast<SM *>(smem_raw);
-  const int table = blockIdx.x / P.ctas, cta = blockIdx.x % P.ctas;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int strip0 = P.strip_base + cta * G;  // strips are numbered over the whole table, passes included
-  int nloc = P.P - strip0;  // strips of this CTA
-  if (nloc > G) nloc = G;
-  const StripTable tb = P.tables[table];
-  const bool cta_left = strip0 > 0, cta_right = strip0 + nloc < P.P;
-
-  for (int i = threadIdx.x; i < LOGTAB_N * LOGTAB_REP8; i += blockDim.x) sm.logtab[i] = P.logtab[i / LOGTAB_REP8];
   if (threadIdx.x < G) {
     auto &sb = sm.sub[threadIdx.x];
     for (int s = 0; s < Cfg::NB; s++) sb.empty_gen[s] = 0;
@@ -848,8 +896,15 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 1) fill_strip_kernel(const Stri
     sm.ring[rg].written = -1;
     sm.ring[rg].taken = (st > 0 && st < P.P) ? strip_geom(P, st).delta - 1 : -1;
   }
-  __syncthreads();
+}
 
+/* one table of the CTA: every warp plays its role; a role that gives up (watchdog, abort flag) simply returns */
+template <int K, int G, bool HAS_S, bool HAS_V, typename OutT>
+__device__ __forceinline__ void cta_roles(StripSmem<K, G, HAS_V> &sm, const StripParams &P, const StripTable &tb, int group,
+                                          int cta, int strip0, int nloc, int round) {
+  using Cfg = StripCfg<K, G, HAS_V>;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool cta_left = strip0 > 0, cta_right = strip0 + nloc < P.P;
   if (warp < G) {
     // producers: warp g on SM sub-partition g
     const int gi = warp;
@@ -863,41 +918,47 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 1) fill_strip_kernel(const Stri
   } else if (warp == ST_LOADER) {
     if (cta_left) {
       const StripGeom g = strip_geom(P, strip0);
-      const int jlast = strip_geom(P, strip0 - 1).nbatch - 1;
+      const int nb_writer = strip_geom(P, strip0 - 1).nbatch;
       GBound gb;
+      int jbase = 0;
       if (cta > 0) {
-        const int bidx = table * P.ctas + cta - 1;
+        const int bidx = group * P.ctas + cta - 1;
         gb.g = P.gring + (size_t)bidx * (ST_NBG * ST_GE);
         gb.mask = ST_NBG - 1;
         gb.taken = P.gtaken + bidx;
+        jbase = round * nb_writer;
       } else {  // first CTA of a later pass
         gb.g = const_cast<uint4 *>(P.carry_in);
         gb.mask = 0xffffffffu;
         gb.taken = NULL;
       }
-      strip_loader(P, &sm.ring[0], g.delta, lane, gb, jlast);
+      strip_loader(P, &sm.ring[0], g.delta, lane, gb, nb_writer - 1, jbase);
     }
   } else if (warp == ST_FLUSHER) {
     if (cta_right) {
       const StripGeom g = strip_geom(P, strip0 + nloc - 1);
       GBound gb;
+      int jbase = 0;
       if (cta + 1 < P.ctas) {
-        const int bidx = table * P.ctas + cta;
+        const int bidx = group * P.ctas + cta;
         gb.g = P.gring + (size_t)bidx * (ST_NBG * ST_GE);
         gb.mask = ST_NBG - 1;
         gb.taken = P.gtaken + bidx;
+        jbase = round * g.nbatch;
       } else {  // last CTA of a pass that is not the last
         gb.g = P.carry_out;
         gb.mask = 0xffffffffu;
         gb.taken = NULL;
       }
-      strip_flusher(P, &sm.ring[nloc], g.nbatch - 1, lane, gb);
+      if (StripCfg<K, G, HAS_V>::FLUSH_FROM_XRING)
+        strip_flusher_xring<K, G, HAS_V>(P, sm.sub[0], &sm.ring[nloc], g.nbatch - 1, lane, gb, jbase);
+      else
+        strip_flusher(P, &sm.ring[nloc], g.nbatch - 1, lane, gb, jbase);
     }
   } else {
-    // consumers: dealt round-robin to the CTA's strips.  A waiter may be at most one phase ahead
-    // of its mbarrier, so a strip gets fewer claimants than it has batch slots.  Consumers fill
-    // the sub-partitions without a producer; a producer's own sub-partition takes only `spread`
-    // of them, so that the recurrence keeps most of its issue slots and FP64 pipe.
+    // consumers: dealt round-robin to the CTA's strips.  Consumers fill the sub-partitions without a
+    // producer; a producer's own sub-partition takes only `spread` of them, so that the recurrence
+    // keeps most of its issue slots and FP64 pipe.
     // consumer index c: warps on the free sub-partitions first, then rows 1..spread of the
     // producers' sub-partitions (the two helper warps excluded)
     int c = -1, ntot = 0;
@@ -930,6 +991,39 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 1) fill_strip_kernel(const Stri
       const StripGeom g = strip_geom(P, strip0 + gi);
       strip_consumer<K, G, HAS_S, HAS_V, OutT>(P, sm.sub[gi], sm.logtab + (lane & (LOGTAB_REP8 - 1)), g, lane, tb, ci, ncs);
     }
+  }
+}
+
+/*
+ * CTA group q = blockIdx.x / ctas fills tables q, q + ngroups, q + 2 ngroups, ... one after the other (the
+ * rounds of a discount sweep in ONE launch: no launch gap, no memset and no pipeline fill / drain between
+ * the tables of a group -- a CTA starts on the next table as soon as its own part of the current one is
+ * done, while its neighbours to the right are still finishing).  Between two tables the CTA's warps meet at
+ * a barrier and the shared state is reset; the global boundary rings run on (strip_loader).
+ */
+template <int K, int G, bool HAS_S, bool HAS_V, typename OutT>
+__global__ void __launch_bounds__(ST_WARPS * 32, 1) fill_strip_kernel(const StripParams P) {
+  using SM = StripSmem<K, G, HAS_V>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int stop;
+  SM &sm = *reinterpret_cast<SM *>(smem_raw);
+  const int group = blockIdx.x / P.ctas, cta = blockIdx.x % P.ctas;
+  const int strip0 = P.strip_base + cta * G;  // strips are numbered over the whole table, passes included
+  int nloc = P.P - strip0;  // strips of this CTA
+  if (nloc > G) nloc = G;
+  for (int i = threadIdx.x; i < LOGTAB_N * LOGTAB_REP8; i += blockDim.x) sm.logtab[i] = P.logtab[i / LOGTAB_REP8];
+  for (int round = 0, table = group; table < P.ntables; ++round, table += P.ngroups) {
+    if (round > 0) {
+      // every warp is done with the previous table; did anybody give up?  (one thread looks, all follow it)
+      __syncthreads();
+      if (threadIdx.x == 0) stop = ld_vol(P.abort_flag);
+      __syncthreads();
+      if (stop) return;
+    }
+    cta_reset<K, G, HAS_V>(sm, P, strip0);
+    __syncthreads();
+    const StripTable tb = P.tables[table];
+    cta_roles<K, G, HAS_S, HAS_V, OutT>(sm, P, tb, group, cta, strip0, nloc, round);
   }
 }
 
@@ -1162,10 +1256,14 @@ inline int strip_fill(StripState *st, const StripFillArgs &A, cudaStream_t strea
   cudaMemsetAsync(st->dbg, 0, (1024 * 8 + 1024 * ST_WARPS * 4) * sizeof(long long), stream);
   P.dbg = st->dbg;
 #endif
-  for (int t0 = 0, pass = 0; t0 < A.ntables && e == cudaSuccess; pass + 1 < passes ? ++pass : (pass = 0, t0 += per_launch)) {
-    const int nt = (A.ntables - t0 < per_launch) ? A.ntables - t0 : per_launch;
-    const bool last_launch = t0 + per_launch >= A.ntables && pass + 1 == passes;
-    P.tables = st->tables + t0;
+  // ONE launch fills all the tables (CTA group q takes tables q, q + per_launch, ...: the kernel's rounds);
+  // only a table wider than a launch's CTAs takes several launches, one per pass over the columns
+  for (int pass = 0; pass < passes && e == cudaSuccess; ++pass) {
+    const int nt = per_launch;  // CTA groups
+    const bool last_launch = pass + 1 == passes;
+    P.tables = st->tables;
+    P.ntables = A.ntables;
+    P.ngroups = nt;
     if (passes > 1) {
       P.strip_base = pass * ctas_pass * pl.G;
       P.ctas = (ctas_total - pass * ctas_pass < ctas_pass) ? ctas_total - pass * ctas_pass : ctas_pass;
@@ -1194,7 +1292,7 @@ inline int strip_fill(StripState *st, const StripFillArgs &A, cudaStream_t strea
       // the abort flag is checked per launch: a later memset must not hide it
       int flag = 0;
       if (last_launch) cudaEventRecord(ev_end, stream);
-      if (A.async_flag && A.ntables <= per_launch && passes == 1) {
+      if (A.async_flag && passes == 1) {
         e = cudaMemcpyAsync(A.async_flag, P.abort_flag, sizeof(int), cudaMemcpyDeviceToHost, stream);
         break;
       }

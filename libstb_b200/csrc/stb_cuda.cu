@@ -610,9 +610,10 @@ struct stb_sweep_dev {
   unsigned N, M;
   int is_float;
   size_t ld;
-  int T;               // slabs == tables per launch
-  void *slab;          // [T][N][ld]
-  double *s1;          // [T][N]
+  int T;               // tables a launch fills side by side (CTA groups)
+  int slabs;           // resident slabs = tables per launch: T groups x rounds (the kernel's rounds, fill_strip.cuh)
+  void *slab;          // [slabs][N][ld]
+  double *s1;          // [slabs][N]
   stb::StripState strip;
   uint32_t *d_n, *d_m;
   size_t npairs, pairs_cap, gather_cap;
@@ -791,17 +792,25 @@ extern "C" stb_sweep_dev_t *stb_cuda_sweep_create(unsigned N, unsigned M, int is
   if (e == cudaSuccess) e = cudaEventCreate(&w->ev1);
   if (e == cudaSuccess) {
     w->T = stb::strip_tables_per_launch(M, w->num_sms);
-    // leave room on the device: never more than a quarter of its memory in slabs
+    // leave room on the device: never more than a quarter of its memory in slabs.  Within that, as many ROUNDS
+    // of T tables as fit (at most 16 rounds, at most 64 GB or a third of what is free): a launch then fills rounds x T tables back to back, and the
+    // launch gap, the ring resets and the pipeline's fill and drain are paid once per launch, not once per T tables
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     const size_t per = (size_t)N * w->ld * (is_float ? 4 : 8);
     while (w->T > 1 && (size_t)w->T * per > free_b / 4) w->T--;
-    e = cudaMalloc(&w->slab, (size_t)w->T * per);
+    size_t budget = free_b / 3 < ((size_t)64 << 30) ? free_b / 3 : ((size_t)64 << 30);
+    int rounds = (int)(budget / ((size_t)w->T * per));
+    if (rounds > 16) rounds = 16;
+    if (const char *sv = getenv("STB_SWEEP_ROUNDS")) rounds = atoi(sv);  // development: 1 = one wave per launch (round-1 behaviour)
+    if (rounds < 1) rounds = 1;
+    w->slabs = w->T * rounds;
+    e = cudaMalloc(&w->slab, (size_t)w->slabs * per);
   }
-  if (e == cudaSuccess) e = cudaMalloc(&w->s1, (size_t)w->T * N * sizeof(double));
-  if (e == cudaSuccess) e = cudaMalloc(&w->d_sum, (size_t)w->T * sizeof(double));
-  if (e == cudaSuccess) e = cudaHostAlloc(&w->h_stage, (size_t)w->T * sizeof(double), cudaHostAllocDefault);
-  if (e == cudaSuccess) w->stage_cap = (size_t)w->T;
+  if (e == cudaSuccess) e = cudaMalloc(&w->s1, (size_t)w->slabs * N * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&w->d_sum, (size_t)w->slabs * sizeof(double));
+  if (e == cudaSuccess) e = cudaHostAlloc(&w->h_stage, (size_t)w->slabs * sizeof(double), cudaHostAllocDefault);
+  if (e == cudaSuccess) w->stage_cap = (size_t)w->slabs;
   if (e != cudaSuccess) {
     fail(e, "stb_cuda_sweep_create");
     stb_cuda_sweep_destroy(w);
@@ -826,7 +835,7 @@ extern "C" int stb_cuda_sweep_set_pairs(stb_sweep_dev_t *w, const uint32_t *n, c
     const size_t nblk = (npairs + 255) / 256;
     CK(cudaMalloc(&w->d_n, npairs * sizeof(uint32_t)));
     CK(cudaMalloc(&w->d_m, npairs * sizeof(uint32_t)));
-    CK(cudaMalloc(&w->d_partial, (size_t)w->T * nblk * sizeof(double)));
+    CK(cudaMalloc(&w->d_partial, (size_t)w->slabs * nblk * sizeof(double)));
     w->pairs_cap = npairs;
   }
   CK(cudaMemcpyAsync(w->d_n, n, npairs * sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
@@ -894,6 +903,8 @@ extern "C" int stb_cuda_sweep_run_dealt(stb_sweep_dev_t *w, const double *a, siz
   }
   if (fill_ms) *fill_ms = 0.f;
   if (!na) return 0;
+  // tables per launch: every resident slab; with per-pair outputs (a [tables][npairs] staging array) one wave of T
+  const size_t chunk = gather_out ? (size_t)w->T : (size_t)w->slabs;
   if (gather_out && w->npairs > w->gather_cap) {
     cudaFree(w->d_gather);
     w->d_gather = NULL;
@@ -906,7 +917,7 @@ extern "C" int stb_cuda_sweep_run_dealt(stb_sweep_dev_t *w, const double *a, siz
   // come back with ONE copy, the watchdog flags of all waves in pinned memory, and the host waits once.
   // (A wave whose results go to pageable caller memory -- gather_out, lastrow_out -- still waits for
   // its own copies.)
-  const size_t nwaves = (na + (size_t)w->T - 1) / (size_t)w->T;
+  const size_t nwaves = (na + chunk - 1) / chunk;
   if (sum_out && na > w->stage_cap) {
     cudaFree(w->d_sum);
     cudaFreeHost(w->h_stage);
@@ -925,11 +936,11 @@ extern "C" int stb_cuda_sweep_run_dealt(stb_sweep_dev_t *w, const double *a, siz
     w->flags_cap = nwaves;
   }
   memset(w->h_flags, 0, nwaves * sizeof(int));
-  std::vector<stb::StripTable> tabs((size_t)w->T);
+  std::vector<stb::StripTable> tabs(chunk);
   CK(cudaEventRecord(w->ev0, w->stream));
   size_t wave = 0;
-  for (size_t j0 = 0; j0 < na; j0 += (size_t)w->T, ++wave) {
-    const int nt = (int)((na - j0 < (size_t)w->T) ? na - j0 : (size_t)w->T);
+  for (size_t j0 = 0; j0 < na; j0 += chunk, ++wave) {
+    const int nt = (int)((na - j0 < chunk) ? na - j0 : chunk);
     for (int t = 0; t < nt; t++) {
       tabs[t].tabS = (char *)w->slab + (size_t)t * slab_elems * es;
       tabs[t].tabV = NULL;

@@ -14,6 +14,8 @@ import time
 
 import numpy as np
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 N, M, A = 200_000, 20_000, 0.7
@@ -36,9 +38,15 @@ def main():
     for f in (R.S_S, R.S_V):
         f.restype, f.argtypes = d, [vp, u, u]
     out = {}
+    which = sys.argv[1] if len(sys.argv) > 1 else "SV"
     for name, flag, fn, count, seed in (("S", 1, R.S_S, N_S, SEED), ("V", 2, R.S_V, N_V, SEED + 1)):
+        if name not in which:
+            continue
         t0 = time.time()
-        sp = R.S_make(N, M, N, M, A, flag)
+        # two rows and columns to spare: S_V treats look-ups within one cell of the table's edge as a request to grow
+        # (lib/stable.c:903) and, at the maximum extent, reads past its rows; cells with n <= N, m <= M do not depend on
+        # the extent of the table they are part of
+        sp = R.S_make(N + 2, M + 2, N + 2, M + 2, A, flag)
         assert sp, "S_make failed (needs ~31 GB)"
         print(f"{name}: reference S_make took {time.time() - t0:.0f} s", file=sys.stderr)
         out[name + "_lastrow"] = np.array([fn(sp, N, m) for m in range(1, M + 1)])
@@ -46,8 +54,25 @@ def main():
         n, m = cells(count, seed)
         out[name + "_cells"] = np.array([fn(sp, int(a), int(b)) for a, b in zip(n, m)])
         R.S_free(sp)
-    np.savez_compressed(os.path.join(HERE, "config2.npz"), N=N, M=M, a=A, seed=SEED, **out)
-    print("wrote", os.path.join(HERE, "config2.npz"), file=sys.stderr)
+    if "O" in which:
+        # V from the oracle's restatement (oracle/stirling_oracle.c, bit-identical to the reference wherever both run,
+        # tests/test_oracle_vs_reference.py): the reference's own V-only table of this size dies in its first S_V call
+        # (its V rows are addressed with 32-bit products: 200 002 x 20 002 > 2^32)
+        from tests import harness
+
+        t0 = time.time()
+        V = np.empty((N, M))
+        harness.oracle().orc_fill_V(N, M, A, V.ctypes.data_as(C.POINTER(C.c_double)), M)
+        print(f"V: oracle fill took {time.time() - t0:.0f} s", file=sys.stderr)
+        out["V_lastrow"] = V[N - 1, :].copy()
+        out["V_lastrow"][0] = 0.0  # m = 1: S_V answers 0
+        out["V_lastcol"] = V[M - 1:, M - 1].copy()
+        n, m = cells(N_V, SEED + 1)
+        out["V_cells"] = V[n.astype(np.int64) - 1, m.astype(np.int64) - 1].copy()
+        del V
+    dst = os.path.join(HERE, "config2.npz" if which == "SV" else f"config2_{which}.npz")
+    np.savez_compressed(dst, N=N, M=M, a=A, seed=SEED, **out)
+    print("wrote", dst, file=sys.stderr)
 
 
 if __name__ == "__main__":

@@ -47,6 +47,50 @@ def test_config2_large_single_table():
     t.free()
 
 
+def _golden_cells(count, seed, N, M):
+    """the seeded (n, m) of tests/golden/make_golden_config2.py"""
+    rng = np.random.default_rng(seed)
+    n = rng.integers(2, N + 1, size=count).astype(np.uint32)
+    m = (2 + (rng.random(count) * (np.minimum(n, M) - 1)).astype(np.uint32)).astype(np.uint32)
+    return n, np.minimum(m, np.minimum(n, M)).astype(np.uint32)
+
+
+def test_config2_against_reference_golden():
+    """SURVEY.md 8d C2 / VERDICT r1 #5: the full config-2 table against values the UNMODIFIED reference produced
+    at that size (tests/golden/config2_S.npz: last row, last column, 10^6 seeded cells of log S, read with the
+    reference's S_S) and, for V, the oracle's restatement (config2_O.npz; the reference's own V-only table of this
+    size crashes in S_V).  Bar: 1e-12 relative (abs floor 1)."""
+    import os
+
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    gs = np.load(os.path.join(gdir, "config2_S.npz"))
+    N, M, a, seed = int(gs["N"]), int(gs["M"]), float(gs["a"]), int(gs["seed"])
+    assert (N, M, a) == (200000, 20000, 0.7)
+    have_v = os.path.exists(os.path.join(gdir, "config2_O.npz"))
+    t = stb.Table(N, M, N, M, a, stb.S_STABLE | (stb.S_UVTABLE if have_v else 0) | stb.S_NOMIRROR)
+    mm = np.arange(1, M + 1, dtype=np.uint32)
+    nn = np.arange(M, N + 1, dtype=np.uint32)
+    worst = {}
+    for name, got, want in (
+        ("S last row", t.S_batch(np.full(M, N, dtype=np.uint32), mm), gs["S_lastrow"]),
+        ("S last column", t.S_batch(nn, np.full(nn.shape[0], M, dtype=np.uint32)), gs["S_lastcol"]),
+        ("S cells", t.S_batch(*_golden_cells(gs["S_cells"].shape[0], seed, N, M)), gs["S_cells"]),
+    ):
+        assert harness.close(got, want).all(), name
+        worst[name] = harness.max_err(got[np.isfinite(want)], want[np.isfinite(want)])
+    if have_v:
+        gv = np.load(os.path.join(gdir, "config2_O.npz"))
+        for name, got, want in (
+            ("V last row", t.V_batch(np.full(M, N, dtype=np.uint32), mm), gv["V_lastrow"]),
+            ("V last column", t.V_batch(nn, np.full(nn.shape[0], M, dtype=np.uint32)), gv["V_lastcol"]),
+            ("V cells", t.V_batch(*_golden_cells(gv["V_cells"].shape[0], seed + 1, N, M)), gv["V_cells"]),
+        ):
+            assert harness.close(got, want).all(), name
+            worst[name] = harness.max_err(got, want)
+    print("config 2 vs golden, max relative error:", worst)
+    t.free()
+
+
 def test_config3_shape_with_V():
     N, M, a = 50000, 5000, 0.7
     t = stb.Table(N, M, N, M, a, stb.S_STABLE | stb.S_UVTABLE)

@@ -87,8 +87,8 @@ __global__ void steps_kernel(long long *cycles, double *sink, int batches, doubl
     const double scn = lane == 0 ? 0.0 : pow2i(sE - elow);
     unsigned nb_addr = lane == 0 ? a_out + 8u : a_xr - 8u;
     if (MODE == 0) {  // MODE 128: steps_var with everything on
-      strip_steps<K, false, false, CP, RS, true>(x, ma, nm1, yin, lane == 0 ? a_out : a_xr + 15 * CP * 8 - 8u, scn, scn, nb_addr, nb_stride, lane == 31, a_xr, a_yr, a_out);
-      strip_steps<K, false, false, CP, RS, false>(x, ma, nm1, yin, 0u, scn, scn, nb_addr, nb_stride, lane == 31, a_xr + 8 * CP * 8,
+      strip_steps<K, false, false, CP, RS, true, true>(x, ma, nm1, yin, lane == 0 ? a_out : a_xr + 15 * CP * 8 - 8u, scn, scn, nb_addr, nb_stride, lane == 31, a_xr, a_yr, a_out);
+      strip_steps<K, false, false, CP, RS, false, true>(x, ma, nm1, yin, 0u, scn, scn, nb_addr, nb_stride, lane == 31, a_xr + 8 * CP * 8,
                                                   a_yr, a_out + 64);
     } else {
       steps_var<K, CP, MODE>(x, ma, nm1, yin, scn, nb_addr, nb_stride, a_xr);
