@@ -24,13 +24,24 @@ constexpr int LOGTAB_N = 257;  // c_i = 1 + i/256, i = 0..256
 // bank j and lane l reads copy l % 16, so the sixteen lanes a shared-memory load serves per pass
 // never collide whatever their mantissas are.  (A single copy of a 16-byte-entry table cost ~2.7
 // passes per load at random indices and was the largest user of shared-memory bandwidth of the fill.)
+// The index is formed from the high word of mant = (hi & 0xFFFFF) | 0x3FF00000 as it stands:
+// (mhi + 0x800) >> 12 = LOGTAB_IDX0 + i serves as table index, and as the reciprocal's argument, with the
+// constants folded into the table's base address and the float's bit pattern.  (Tried: the interval's MIDPOINT
+// instead of the nearest c_i -- no rounding add, one instruction per cell less -- but a power of two then no
+// longer comes out as an exact multiple of ln2, and log S^2_1 = log 1 at a = 0 must print as 0 like the
+// reference's; the instruction made no measurable difference.)
 constexpr int LOGTAB_REP8 = 16;
+constexpr unsigned LOGTAB_IDX0 = 0x3FF00u;  // ((high word of a double in [1,2)) + 0x800) >> 12 = LOGTAB_IDX0 + i
 
-__device__ __forceinline__ double logtab_inv_c(int idx) {  // rcp(1 + idx/256) as a double, idx = 0..256
-  float invf;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(invf) : "f"(__int_as_float(0x3F800000 + (idx << 15))));
-  const unsigned fb = __float_as_uint(invf);  // positive normal: widen by moving the bits
+__device__ __forceinline__ double logtab_widen(float invf) {  // a positive normal float as a double: move the bits
+  const unsigned fb = __float_as_uint(invf);
   return __hiloint2double((int)((fb >> 3) + 0x38000000u), (int)(fb << 29));
+}
+/* rcp(c_i) from idxh = LOGTAB_IDX0 + i: the float c_i has the bits 0x3F800000 + (i << 15) */
+__device__ __forceinline__ double logtab_inv_h(unsigned idxh) {
+  float invf;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(invf) : "f"(__uint_as_float((idxh << 15) + (0x3F800000u - (LOGTAB_IDX0 << 15)))));
+  return logtab_widen(invf);
 }
 constexpr long long FILL_WATCHDOG = 6000000000LL;  // cycles a wait may last before the fill aborts
 
@@ -78,26 +89,27 @@ __device__ __forceinline__ double div_pos(double x, double d) {
  * log(x * 2^E) for x > 0 finite normal, E given as kbias = E + 0x80000000 - 1023 (mod 2^32): then
  * (hi >> 20) + kbias is the low word of the double 2^52 + 2^31 + (E + k), k the exponent of x, and
  * one subtraction of that constant gives E + k exactly (|E + k| < 2^31).
- * Table-driven: x = 2^k * mant, mant in [1,2); c = 1 + i/256 nearest to mant; r = mant*rcp(c) - 1
- * (|r| <= 2^-9 + 2^-23, one FMA); log(mant) = log1p(r) + T[i]; result = (E+k) ln2 + T[i] + log1p(r).
- * mant == 1 gives exactly (E+k) ln2, so S^n_n comes out as +0.0.  (tab points at this lane's copy,
- * entries REP apart.)
+ * Table-driven: x = 2^k * mant, mant in [1,2); c = 1 + i/256 nearest to mant;
+ * r = mant*rcp(c) - 1 (|r| <= 2^-9 + 2^-23, one FMA); log(mant) = log1p(r) + T[i]; result =
+ * (E+k) ln2 + T[i] + log1p(r).  mant == 1 gives exactly (E+k) ln2, so S^n_n comes out as +0.0.
+ * tab_s: SHARED address of this lane's copy of the table (entries REP apart) minus LOGTAB_IDX0 entries, so
+ * that the index needs no offset.
  */
 template <int REP>
-__device__ __forceinline__ double log_scaled_r(double x, unsigned kbias, const double *tab) {
-  const int hi = __double2hiint(x), lo = __double2loint(x);
-  const int frac = hi & 0xFFFFF;
-  const int idx = (frac + 0x800) >> 12;
-  const double mant = __hiloint2double(frac | 0x3FF00000, lo);
-  const double log_c = tab[idx * REP];
-  const double r = fma(mant, logtab_inv_c(idx), -1.0);
+__device__ __forceinline__ double log_scaled_r(double x, unsigned kbias, unsigned tab_s) {
+  const unsigned hi = (unsigned)__double2hiint(x);
+  const unsigned mhi = (hi & 0xFFFFFu) | 0x3FF00000u;
+  const unsigned idxh = (mhi + 0x800u) >> 12;
+  const double mant = __hiloint2double((int)mhi, __double2loint(x));
+  double log_c;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(log_c) : "r"(tab_s + idxh * (unsigned)(REP * 8)));
+  const double r = fma(mant, logtab_inv_h(idxh), -1.0);
   // log1p(r) = r (1 - r/2 + r^2/3 - r^3/4) + O(r^5/5), |r| <= 2^-9 + 2^-23: truncation < 6e-15
-  // absolute, far inside the 1e-12 bar; seven FP64 instructions in all (the issue rate of the
-  // consumers' FP64 instructions is what binds the kernel, profiles/README.md)
+  // absolute, far inside the 1e-12 bar; seven FP64 instructions in all
   double t = fma(r, -0.25, 1.0 / 3.0);
   t = fma(r, t, -0.5);
   t = fma(r, t, 1.0);
-  const double Ek = __hiloint2double(0x43300000, (int)(((unsigned)hi >> 20) + kbias)) - LOG_EBIAS;
+  const double Ek = __hiloint2double(0x43300000, (int)((hi >> 20) + kbias)) - LOG_EBIAS;
   return fma(r, t, fma(Ek, 0.693147180559945309417232, log_c));
 }
 
@@ -105,7 +117,7 @@ __device__ __forceinline__ double log_scaled_r(double x, unsigned kbias, const d
 __global__ void logtab8_build_kernel(double *tab) {
   const int i = threadIdx.x + blockIdx.x * blockDim.x;
   if (i >= LOGTAB_N) return;
-  const double inv = logtab_inv_c(i);
+  const double inv = logtab_inv_h(LOGTAB_IDX0 + (unsigned)i);
   tab[i] = (inv == 1.0) ? 0.0 : -log(inv);
 }
 

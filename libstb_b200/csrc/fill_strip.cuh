@@ -59,7 +59,13 @@ constexpr int ST_NJ = 16;         // producer batches of per-lane exponents kept
 #ifndef ST_WARPS_OVERRIDE
 #define ST_WARPS_OVERRIDE 16
 #endif
-constexpr int ST_WARPS = ST_WARPS_OVERRIDE;  // warps per CTA
+constexpr int ST_WARPS = ST_WARPS_OVERRIDE;  // warps per CTA of a kernel that makes S and V
+#ifndef ST_WARPS1_OVERRIDE
+#define ST_WARPS1_OVERRIDE 20
+#endif
+constexpr int ST_WARPS1 = ST_WARPS1_OVERRIDE;  // ... of one that makes S or V alone: its consumers need fewer registers, twenty warps fit (15 consumers, 5 per free sub-partition; measured on config 2: S 9.36 -> 9.06 ms on the same box; with S and V the registers of 20 warps spill: 13.7 -> 15.1 ms)
+constexpr int ST_MAXW = ST_WARPS1 > ST_WARPS ? ST_WARPS1 : ST_WARPS;
+__host__ __device__ constexpr int strip_warps(bool has_s, bool has_v) { return (has_s && has_v) ? ST_WARPS : ST_WARPS1; }
 #ifndef ST_LOADER_OVERRIDE
 #define ST_LOADER_OVERRIDE 4
 #define ST_FLUSHER_OVERRIDE 8
@@ -487,7 +493,18 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
     // G > 1: the boundary ring holds ST_NBR batches
     const int need_in = has_left ? jb : NO_NEED, need_out = has_right ? p - (OUT ? ST_NBR : NB / 2) : NO_NEED;
     if (gen_next.x < gen_need || gen_next.y < gen_need || c_in < need_in || c_out < need_out) {
+#ifdef STB_PROFILE_PRODUCER
+      {  // which condition holds the producer up (cycles attributed to the first one found wanting)
+        const long long tw0 = clock64();
+        const int2 gq = lds_v2s32(a_gen + s0 * 4);
+        const int wq = has_left ? lds_s32(a_in_written) : 0, tq = has_right ? lds_s32(a_out_taken) : 0;
+        const int why = (gq.x < gen_need || gq.y < gen_need) ? 1 : (wq < need_in ? 2 : (tq < need_out ? 6 : 7));
+        if (!producer_wait(a_gen + s0 * 4, gen_need, a_in_written, need_in, a_out_taken, need_out, P.abort_flag)) return;
+        dbgacc[why] += clock64() - tw0;
+      }
+#else
       if (!producer_wait(a_gen + s0 * 4, gen_need, a_in_written, need_in, a_out_taken, need_out, P.abort_flag)) return;
+#endif
       c_in = max(c_in, need_in);
       c_out = max(c_out, need_out);
     }
@@ -564,6 +581,7 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
   if (lane0 && P.dbg) {
     long long *d = P.dbg + ((size_t)blockIdx.x * G + (threadIdx.x >> 5)) * 8;
     for (int i = 0; i < 5; i++) d[i] = dbgacc[i];
+    d[3] = dbgacc[3] + (dbgacc[6] << 40);  // (the cycles spent waiting for the flusher travel in the upper bits)
     d[6] = g.nbatch;
     unsigned long long gt_end;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_end));
@@ -581,7 +599,9 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
  */
 __device__ __forceinline__ unsigned long long gaddr(const void *p) { return (unsigned long long)__cvta_generic_to_global(p); }
 __device__ __forceinline__ unsigned long long row_addr(unsigned long long base, unsigned pitch_bytes, unsigned i) {
-  return base + (unsigned long long)(i * pitch_bytes);  // i * pitch is loop-invariant: kept in registers
+  unsigned long long r;  // base + i * pitch as ONE wide multiply-add (i is a constant after unrolling)
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(pitch_bytes), "r"(i), "l"(base));
+  return r;
 }
 __device__ __forceinline__ void stg(unsigned long long a, double v, double *) {
   asm volatile("st.global.f64 [%0], %1;" ::"l"(a), "d"(v) : "memory");
@@ -591,19 +611,99 @@ __device__ __forceinline__ void stg(unsigned long long a, double v, float *) {
 }
 
 // ---- consumer ----------------------------------------------------------------------------------------
+/*
+ * The consumers are bound by instruction issue (ncu, profiles/README.md: every instruction of the per-unit code costs
+ * about the same, taken branches and dependent address arithmetic more), so the loop over units is kept as lean as
+ * it gets: shared addresses are 32-bit words formed once, the slow paths (waiting for the producer, the strip's
+ * triangle and last rows) are functions of their own, the table stores are predicated instead of branched around,
+ * what only the table's first strip does (the S1 column, no V in column 1) is a template flag, and the slot release
+ * is one predicated fence + reduction.
+ */
+/* one more unit of a ring slot is finished: the warp's ring reads are ordered in front of the count (release, cta scope) */
+__device__ __forceinline__ void slot_release(unsigned gen_s, int lane) {
+  __syncwarp();
+#if STB_FENCES
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %1, 0;\n\t@p fence.acq_rel.cta;\n\t@p red.shared.add.u32 [%0], 1;\n\t}" ::"r"(gen_s), "r"(lane) : "memory");
+#else
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %1, 0;\n\t@p red.shared.add.u32 [%0], 1;\n\t}" ::"r"(gen_s), "r"(lane) : "memory");
+#endif
+}
+
+/* slow path of a consumer's wait for the producer: polls the progress word; returns what it saw last (< need: the fill was aborted) */
+__device__ __noinline__ int consumer_wait(unsigned prog_s, int need, int *abort_flag) {
+  const long long t0 = clock64();
+  unsigned spins = 0;
+  int v;
+  for (;;) {
+    v = lds_s32(prog_s);
+    if (v >= need) break;
+    __nanosleep(ST_CONS_SLEEP);
+    if ((++spins & 1023u) == 0) {
+      const int bad = ld_vol(abort_flag) || (clock64() - t0 > FILL_WATCHDOG);
+      if (__any_sync(0xffffffffu, bad)) {
+        if ((threadIdx.x & 31) == 0) atomicExch(abort_flag, 1);
+        break;
+      }
+    }
+  }
+  return v;
+}
+
+__device__ __forceinline__ void stg_if(unsigned long long a, double v, bool p, double *) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.f64 [%0], %1;\n\t}" ::"l"(a), "d"(v), "r"((unsigned)p) : "memory");
+}
+__device__ __forceinline__ void stg_if(unsigned long long a, double v, bool p, float *) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.f32 [%0], %1;\n\t}" ::"l"(a), "f"((float)v), "r"((unsigned)p) : "memory");
+}
+
+/* a unit on the strip's triangle (column col exists from row r = col on) or on the table's last rows: rare, not inlined */
 template <int K, int G, bool HAS_S, bool HAS_V, typename OutT>
-__device__ void strip_consumer(const StripParams &P, StripSub<K, G, HAS_V> &sb, const double *logtab,
-                               const StripGeom &g, int lane, const StripTable &tb, const int ci, const int ncs) {
+__device__ __noinline__ void consumer_edge_unit(const StripParams &P, StripSub<K, G, HAS_V> &sb, const unsigned logtab,
+                                                const StripGeom &g, int lane, const StripTable &tb, int q, int kk) {
   using Cfg = StripCfg<K, G, HAS_V>;
   constexpr int CP = Cfg::CP, NB = Cfg::NB;
-  const int M = P.M;
-  int cvalid = M - g.rs;  // columns of this strip that exist
+  int cvalid = P.M - g.rs;
   if (cvalid > P.C) cvalid = P.C;
   OutT *tabS = (OutT *)tb.tabS;
   OutT *tabV = (OutT *)tb.tabV;
   const bool first_strip = (g.rs == 0);
-  const unsigned ld32 = (unsigned)P.ld;  // 8 rows x ld elements stay far below 2^32
-  const unsigned pitchb = ld32 * (unsigned)sizeof(OutT);  // row pitch in bytes (strip_fill checks ld * 8 < 2^32)
+  const int r0 = q * ST_RB;
+  const int col = lane + 32 * kk;
+  if (col >= cvalid) return;
+  const int pl = col / K, kq = col - pl * K;
+  const int toff = r0 + pl + g.phi;
+  const int ub = ((toff >> 3) % NB) * ST_RB + (toff & 7);
+  const volatile double *xc = &sb.xring[ub * CP + col];
+  const volatile double *yc = &sb.yring[HAS_V ? ub * 32 + pl : 0];
+  const volatile unsigned *er = sb.ering;
+  const size_t cell0 = (size_t)(g.rs + r0) * P.ld + (size_t)(g.rs + col);  // row n-1 = rs+r, column m-1
+  for (int i = 0; i < ST_RB; i++) {
+    const int r = r0 + i;
+    if (r >= g.R || col > r) continue;
+    const double xv = xc[i * CP];
+    const size_t off = cell0 + (size_t)i * P.ld;
+    if (HAS_S) {
+      const int j = (toff + i) >> ST_SH;
+      // S^n_n = 1 (the strip's own diagonal: column col in its row col) is stored as exactly +0.0
+      const double v = (col == r) ? 0.0 : log_scaled_r<LOGTAB_REP8>(xv, er[(j & (ST_NJ - 1)) * 32 + pl], logtab);
+      st_out(tabS + off, v);
+      if (first_strip && col == 0) tb.s1[r] = v;
+    }
+    if (HAS_V && !(first_strip && col == 0)) {
+      const double den = (kq == 0) ? yc[i * 32] : xc[i * CP - 1];
+      st_out(tabV + off, div_pos(xv, den));
+    }
+  }
+}
+
+template <int K, int G, bool HAS_S, bool HAS_V, typename OutT, bool FIRST>
+__device__ void strip_consumer(const StripParams &P, StripSub<K, G, HAS_V> &sb, const unsigned logtab,
+                               const StripGeom &g, int lane, const StripTable &tb, const int ci, const int ncs) {
+  using Cfg = StripCfg<K, G, HAS_V>;
+  constexpr int CP = Cfg::CP, NB = Cfg::NB;
+  int cvalid = P.M - g.rs;  // columns of this strip that exist
+  if (cvalid > P.C) cvalid = P.C;
+  const unsigned pitchb = (unsigned)P.ld * (unsigned)sizeof(OutT);  // row pitch in bytes (strip_fill checks ld * 8 < 2^32)
 
 #ifdef STB_PROFILE_PRODUCER
   long long cacc[4] = {0, 0, 0, 0};
@@ -626,86 +726,93 @@ __device__ void strip_consumer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
   int q = ci / U, kk = ci - q * U;
   const int dq = ncs / U, dk = ncs - dq * U;
   int prog = -1;  // the producer's progress as last seen
+  // addresses the loop works with: shared ones as 32-bit words, the table's as 64-bit global addresses of the
+  // strip's cell (r = 0, col = 0)
+  const unsigned xring_s = smem_u32(&sb.xring[0]), ering_s = smem_u32(&sb.ering[0]);
+  const unsigned prog_s = smem_u32(&sb.progress), gen_s = smem_u32(&sb.empty_gen[0]);
+  constexpr unsigned ES = (unsigned)sizeof(OutT);
+  const unsigned long long gS0 = HAS_S ? gaddr(tb.tabS) + ((unsigned long long)g.rs * P.ld + (unsigned)g.rs) * ES : 0ull;
+  const unsigned long long gV0 = HAS_V ? gaddr(tb.tabV) + ((unsigned long long)g.rs * P.ld + (unsigned)g.rs) * ES : 0ull;
+  // rows 8q .. 8q+7 of every lane are in the ring once the producer has finished the batch that
+  // holds step 8q+7 + (L-1) + phi (the last lane runs L-1 rows behind the first); a partial last
+  // row batch is complete with the last producer batch
+  const int c_need = ST_RB - 1 + P.L - 1 + g.phi, last_b = g.nbatch - 1;
+  const int r_fast_hi = g.R - ST_RB;  // a unit is off the edges when cvalid <= r0 <= R - 8
   for (; q < g.QT;) {
-    const int slot = q % NB;
     ST_CTICK(0);
-    // rows 8q .. 8q+7 of every lane are in the ring once the producer has finished the batch that
-    // holds step 8q+7 + (L-1) + phi (the last lane runs L-1 rows behind the first); a partial last
-    // row batch is complete with the last producer batch
-    int p_need = ((q * ST_RB + ST_RB - 1 + P.L - 1 + g.phi) >> ST_SH);
-    if (p_need > g.nbatch - 1) p_need = g.nbatch - 1;
-    if (!ctr_wait<false, ST_CONS_SLEEP>(&sb.progress, p_need, P.abort_flag, prog)) return;
-    ST_CTICK(1);  // wait for the rows
     const int r0 = q * ST_RB;
-    const bool fast = (r0 >= cvalid - 1) && (r0 + ST_RB <= g.R);
-    {
+    const int p_need = min((r0 + c_need) >> ST_SH, last_b);
+#ifndef STB_C_CALL_WAIT  // (the wait inlined measured 1-2 % faster than the call on config 2)
+    if (!ctr_wait<false, ST_CONS_SLEEP>(&sb.progress, p_need, P.abort_flag, prog)) return;
+#else
+    if (prog < p_need) {
+      prog = consumer_wait(prog_s, p_need, P.abort_flag);
+      if (prog < p_need) return;
+    }
+#endif
+    ST_CTICK(1);  // wait for the rows
+    if (r0 >= cvalid && r0 <= r_fast_hi) {
+      // (rows strictly below the strip's diagonal: the diagonal itself is the edge path's)
+      // (tried: a variant for strips whose consumers are a multiple of the column blocks -- every warp keeps its
+      // block, the column's geometry hoisted out of the loop: 4 % SLOWER on config 2, 9.44 against 9.04 ms)
       const int col = lane + 32 * kk;
       const int pl = col / K;
-      const int kq = col % K;
       const bool lane_ok = col < cvalid;
-      const size_t cell0 = (size_t)(g.rs + r0) * P.ld + (size_t)(g.rs + col);  // row n-1 = rs+r, column m-1
       // producer lane pl made rows r0..r0+7 at steps toff..toff+7 (ring rows ub..ub+7, never
       // wrapping thanks to the duplicate rows); its exponent changes at most once on the way
       const int toff = r0 + pl + g.phi;
-      const int j0 = toff >> ST_SH, thr = ST_B - (toff & (ST_B - 1));
-      const int ub = ((toff >> 3) % NB) * ST_RB + (toff & 7);
-      const double *xc = &sb.xring[ub * CP + col];
-      const double *yc = &sb.yring[HAS_V ? ub * 32 + pl : 0];
-      if (fast) {
-        double xv[ST_RB];
+      const int ub = (NB == 16) ? (toff & (16 * ST_RB - 1)) : ((toff >> 3) % NB) * ST_RB + (toff & 7);
+      const unsigned xa = xring_s + (unsigned)(ub * CP + col) * 8u;
+      // a 1 the compiler cannot see through, and not loop-invariant either: row i+1 of a unit is stored at (address
+      // of row i) + pitch * one, ONE wide multiply-add per row (a constant or hoisted factor becomes an add with
+      // carry: two instructions)
+      const unsigned one = 1u + ((unsigned)q >> 28);
+      double xv[ST_RB];
 #pragma unroll
-        for (int i = 0; i < ST_RB; i++) xv[i] = xc[i * CP];
-        if (HAS_S) {
-          const unsigned Ea = sb.ering[(j0 & (ST_NJ - 1)) * 32 + pl];
-          const unsigned Eb = sb.ering[((j0 + 1) & (ST_NJ - 1)) * 32 + pl];
-          double v[ST_RB];
+      for (int i = 0; i < ST_RB; i++) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(xv[i]) : "r"(xa + (unsigned)(i * CP * 8)));
+      if (HAS_S) {
+        const unsigned ja = ((unsigned)toff >> ST_SH) & (ST_NJ - 1), jb = (ja + 1) & (ST_NJ - 1);
+        const unsigned sh = (unsigned)toff & (ST_B - 1);  // row i is of the next batch when i + sh >= 16
+        unsigned Ea, Eb;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Ea) : "r"(ering_s + (ja * 32 + (unsigned)pl) * 4u));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Eb) : "r"(ering_s + (jb * 32 + (unsigned)pl) * 4u));
+        double v[ST_RB];
 #pragma unroll
-          for (int i = 0; i < ST_RB; i++) v[i] = log_scaled_r<LOGTAB_REP8>(xv[i], (i >= thr) ? Eb : Ea, logtab);
-          if (lane_ok) {
-            const unsigned long long gS = gaddr(tabS) + cell0 * sizeof(OutT);
+        for (int i = 0; i < ST_RB; i++) v[i] = log_scaled_r<LOGTAB_REP8>(xv[i], (i + sh >= (unsigned)ST_B) ? Eb : Ea, logtab);
+        unsigned long long ga = row_addr(gS0, pitchb, (unsigned)r0) + (unsigned)col * ES;
 #pragma unroll
-            for (int i = 0; i < ST_RB; i++) stg(row_addr(gS, pitchb, (unsigned)i), v[i], (OutT *)nullptr);
-            if (first_strip && col == 0) {
-#pragma unroll
-              for (int i = 0; i < ST_RB; i++) tb.s1[r0 + i] = v[i];
-            }
-          }
-        }
-        if (HAS_V) {
-          double den[ST_RB];
-#pragma unroll
-          for (int i = 0; i < ST_RB; i++) den[i] = (kq == 0) ? yc[i * 32] : xc[i * CP - 1];
-          if (lane_ok && !(first_strip && col == 0)) {
-            const unsigned long long gV = gaddr(tabV) + cell0 * sizeof(OutT);
-#pragma unroll
-            for (int i = 0; i < ST_RB; i++) stg(row_addr(gV, pitchb, (unsigned)i), div_pos(xv[i], den[i]), (OutT *)nullptr);
-          }
-        }
-      } else if (lane_ok) {
-        // ---- edges: the strip's triangle (column col exists from row r = col on), last rows ----
         for (int i = 0; i < ST_RB; i++) {
-          const int r = r0 + i;
-          if (r >= g.R || col > r) continue;
-          const double xv = xc[i * CP];
-          const size_t off = cell0 + (size_t)i * P.ld;
-          if (HAS_S) {
-            const int j = (toff + i) >> ST_SH;
-            const double v = log_scaled_r<LOGTAB_REP8>(xv, sb.ering[(j & (ST_NJ - 1)) * 32 + pl], logtab);
-            st_out(tabS + off, v);
-            if (first_strip && col == 0) tb.s1[r] = v;
-          }
-          if (HAS_V && !(first_strip && col == 0)) {
-            const double den = (kq == 0) ? yc[i * 32] : xc[i * CP - 1];
-            st_out(tabV + off, div_pos(xv, den));
+          stg_if(ga, v[i], lane_ok, (OutT *)nullptr);
+          if (i + 1 < ST_RB) ga = row_addr(ga, pitchb, one);
+        }
+        if (FIRST && kk == 0) {  // S1: log S^n_1 in FP64 whatever the table stores
+          if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < ST_RB; i++) tb.s1[r0 + i] = v[i];
           }
         }
       }
+      if (HAS_V) {
+        const int kq = col - pl * K;
+        double den[ST_RB];
+        // the cell to the left: the lane's own producer lane made it (same units, one column to the left in the x
+        // ring) unless the column is its producer lane's first -- then it is in the y ring, converted to the lane's
+        // units by the producer.  Two predicated loads with immediate offsets per row.
+        const double *xcm = &sb.xring[ub * CP + col - 1], *ycm = &sb.yring[HAS_V ? ub * 32 + pl : 0];
+#pragma unroll
+        for (int i = 0; i < ST_RB; i++) den[i] = (kq == 0) ? ycm[i * 32] : xcm[i * CP];
+        const bool v_ok = FIRST ? (lane_ok && col != 0) : lane_ok;
+        unsigned long long ga = row_addr(gV0, pitchb, (unsigned)r0) + (unsigned)col * ES;
+#pragma unroll
+        for (int i = 0; i < ST_RB; i++) {
+          stg_if(ga, div_pos(xv[i], den[i]), v_ok, (OutT *)nullptr);
+          if (i + 1 < ST_RB) ga = row_addr(ga, pitchb, one);
+        }
+      }
+    } else {
+      consumer_edge_unit<K, G, HAS_S, HAS_V, OutT>(P, sb, logtab, g, lane, tb, q, kk);
     }
-    __syncwarp();
-    if (lane == 0) {
-      release_cta();  // the unit's ring reads are ordered in front of the slot's release
-      atomicAdd(&sb.empty_gen[slot], 1);
-    }
+    slot_release(gen_s + ((unsigned)q % (unsigned)NB) * 4u, lane);
     ST_CTICK(2);  // the unit
     q += dq;
     kk += dk;
@@ -719,7 +826,7 @@ __device__ void strip_consumer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
   }
 #ifdef STB_PROFILE_PRODUCER
   if (lane == 0 && P.dbg) {
-    long long *d = P.dbg + 1024 * 8 + ((size_t)blockIdx.x * ST_WARPS + (threadIdx.x >> 5)) * 4;
+    long long *d = P.dbg + 1024 * 8 + ((size_t)blockIdx.x * ST_MAXW + (threadIdx.x >> 5)) * 4;
     for (int i = 0; i < 4; i++) d[i] = cacc[i];
   }
 #endif
@@ -965,7 +1072,7 @@ __device__ __forceinline__ void cta_roles(StripSmem<K, G, HAS_V> &sm, const Stri
     {
       int nfree = 0, nshared = 0, mine = -1;
       bool mine_free = false;
-      for (int w = G; w < ST_WARPS; w++) {
+      for (int w = G; w < strip_warps(HAS_S, HAS_V); w++) {
         if (w == ST_LOADER || w == ST_FLUSHER) continue;
         const bool fr = (w & 3) >= G;
         if (!fr && G < 4 && (w >> 2) > P.spread) continue;
@@ -989,7 +1096,11 @@ __device__ __forceinline__ void cta_roles(StripSmem<K, G, HAS_V> &sm, const Stri
     if (ncs > P.ncons) ncs = P.ncons;
     if (gi < nloc && ci < ncs) {
       const StripGeom g = strip_geom(P, strip0 + gi);
-      strip_consumer<K, G, HAS_S, HAS_V, OutT>(P, sm.sub[gi], sm.logtab + (lane & (LOGTAB_REP8 - 1)), g, lane, tb, ci, ncs);
+      const unsigned ltab = smem_u32(sm.logtab + (lane & (LOGTAB_REP8 - 1))) - LOGTAB_IDX0 * (LOGTAB_REP8 * 8);
+      if (g.rs == 0)
+        strip_consumer<K, G, HAS_S, HAS_V, OutT, true>(P, sm.sub[gi], ltab, g, lane, tb, ci, ncs);
+      else
+        strip_consumer<K, G, HAS_S, HAS_V, OutT, false>(P, sm.sub[gi], ltab, g, lane, tb, ci, ncs);
     }
   }
 }
@@ -1002,7 +1113,7 @@ __device__ __forceinline__ void cta_roles(StripSmem<K, G, HAS_V> &sm, const Stri
  * a barrier and the shared state is reset; the global boundary rings run on (strip_loader).
  */
 template <int K, int G, bool HAS_S, bool HAS_V, typename OutT>
-__global__ void __launch_bounds__(ST_WARPS * 32, 1) fill_strip_kernel(const StripParams P) {
+__global__ void __launch_bounds__(strip_warps(HAS_S, HAS_V) * 32, 1) fill_strip_kernel(const StripParams P) {
   using SM = StripSmem<K, G, HAS_V>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int stop;
@@ -1090,7 +1201,7 @@ inline cudaError_t launch_strip(const StripParams &P, int nctas, cudaStream_t st
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   void *args[] = {(void *)&P};
-  return cudaLaunchCooperativeKernel((void *)kern, dim3(nctas), dim3(ST_WARPS * 32), args, smem, stream);
+  return cudaLaunchCooperativeKernel((void *)kern, dim3(nctas), dim3(strip_warps(HAS_S, HAS_V) * 32), args, smem, stream);
 }
 
 template <int K, int G>
@@ -1252,8 +1363,8 @@ inline int strip_fill(StripState *st, const StripFillArgs &A, cudaStream_t strea
   if (const char *s = getenv("STB_STRIP_SPREAD")) P.spread = atoi(s);
   P.dbg = NULL;
 #ifdef STB_PROFILE_PRODUCER
-  if (!st->dbg) cudaMalloc(&st->dbg, (1024 * 8 + 1024 * ST_WARPS * 4) * sizeof(long long));
-  cudaMemsetAsync(st->dbg, 0, (1024 * 8 + 1024 * ST_WARPS * 4) * sizeof(long long), stream);
+  if (!st->dbg) cudaMalloc(&st->dbg, (1024 * 8 + 1024 * ST_MAXW * 4) * sizeof(long long));
+  cudaMemsetAsync(st->dbg, 0, (1024 * 8 + 1024 * ST_MAXW * 4) * sizeof(long long), stream);
   P.dbg = st->dbg;
 #endif
   // ONE launch fills all the tables (CTA group q takes tables q, q + per_launch, ...: the kernel's rounds);
@@ -1300,11 +1411,11 @@ inline int strip_fill(StripState *st, const StripFillArgs &A, cudaStream_t strea
       if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
 #ifdef STB_PROFILE_PRODUCER
       if (e == cudaSuccess && getenv("STB_PROFILE_PRINT")) {
-        static long long h[1024 * 8 + 1024 * ST_WARPS * 4];
+        static long long h[1024 * 8 + 1024 * ST_MAXW * 4];
         cudaMemcpy(h, st->dbg, sizeof h, cudaMemcpyDeviceToHost);
         for (int c : {0, nctas / 2}) {
-          for (int w = 0; w < ST_WARPS; w++) {
-            const long long *d = h + 1024 * 8 + ((size_t)c * ST_WARPS + w) * 4;
+          for (int w = 0; w < ST_MAXW; w++) {
+            const long long *d = h + 1024 * 8 + ((size_t)c * ST_MAXW + w) * 4;
             if (c < 1024 && d[3] > 0)
               fprintf(stderr, "cta %3d consumer warp %2d units %6lld cycles/unit: claim %.0f wait %.0f work %.0f\n", c, w, d[3],
                       (double)d[0] / d[3], (double)d[1] / d[3], (double)d[2] / d[3]);
@@ -1321,7 +1432,8 @@ inline int strip_fill(StripState *st, const StripFillArgs &A, cudaStream_t strea
             fprintf(stderr,
                     "cta %3d producer %d batches %6.0f cycles/batch: flow-control %.0f - %.0f - %.0f setup %.0f "
                     "steps %.0f publish %.0f | busy %.1f us\n",
-                    c, gi, nb, d[0] / nb, d[1] / nb, d[2] / nb, d[3] / nb, d[4] / nb, d[5] / nb, d[7] / 1e3);
+                    c, gi, nb, d[0] / nb, d[1] / nb, d[2] / nb, (d[3] & ((1ll << 40) - 1)) / nb, d[4] / nb, d[5] / nb, d[7] / 1e3);
+            fprintf(stderr, "          (flow control: ring slots %.0f, left boundary %.0f, flusher %.0f)\n", d[1] / nb, d[2] / nb, (d[3] >> 40) / nb);
           }
         }
       }
