@@ -119,6 +119,18 @@ typedef struct stb_sample_stats {
 int stb_samplea_batch(double *a, size_t C, int I, const int *K, const scnt_int *T, scnt_int **n, stcnt_int **t,
                       const double *bpar, int bpar_per_chain, uint64_t *rng, int loops, stb_sample_stats *st);
 
+/*
+ * samplea2 (lib/samplea.c:227-341, the reference's -DSAMPLEA_M build) for C chains over the same statistics:
+ * chain c samples the seat partition of every node with 1 < t < n against its OWN Stirling table at a[c] (one
+ * table per chain out of a discount sweep; the scalar samplea2 is handed the caller's table), drawing its
+ * uniforms from rng[c] in the scalar call's order, and then makes one slice step on the partition's
+ * likelihood -- a device reduction over the chain's histogram of sampled table sizes.  The partition mode is
+ * stb_set_partition_mode's.  Chain c's new discount and stream equal the scalar samplea2's on a table at a[c]
+ * with the stream rng[c].  Return values as stb_samplea_batch.
+ */
+int stb_samplea2_batch(double *a, size_t C, int I, const int *K, const scnt_int *T, scnt_int **n, stcnt_int **t,
+                       const double *bpar, int bpar_per_chain, uint64_t *rng, int loops, stb_sample_stats *st);
+
 /* sampleb for C chains: b[c] in/out, apar[c] the chain's discount, rng[c] in/out */
 int stb_sampleb_batch(double *b, size_t C, int I, double shape, double scale, const scnt_int *N, const scnt_int *T,
                       const double *apar, uint64_t *rng, int loops, stb_sample_stats *st);

@@ -117,6 +117,28 @@ int stb_sweep_multi_devices(const stb_sweep_multi_t *w);
 void stb_sweep_multi_free(stb_sweep_multi_t *w);
 
 /*
+ * A device-side consumer of the V table: table-indicator Gibbs sweeps of a Pitman-Yor /
+ * Dirichlet-process mixture over R restaurants, reading V^n_m straight from the table's slab in device memory
+ * -- the per-token update of the reference's demo (test/demo.c:405-434), whose inner operation is one scalar
+ * S_V look-up per token on the host.  Restaurant j serves D dishes: n[j*D + i] customers eat dish i at
+ * t[j*D + i] tables (1 <= t <= n wherever n > 0), T[j] = sum_i t[j*D + i]; its tokens, in the order they are
+ * visited, are the dishes tok_dish[tok_off[j] .. tok_off[j+1]).  For a token of dish i with n > 1 a sweep
+ *   - removes its table indicator with probability (t - 1)/(n - 1)            (drawn only when t > 1),
+ *   - adds one with probability one/(one + 1), one = (float)(H[i] (b + T a) t/(n - t + 1) V^n_{t+1}),
+ * a = the table's discount, b = bpar, the arithmetic operation by operation as in the demo.  Restaurants are
+ * independent given (a, b, H): with shared_stream == 0 each runs on its own 48-bit stream rng[j] (the state of a
+ * stb_rng48_t, i.e. what seed48 would be handed) -- one thread per restaurant, `sweeps` sweeps per launch.
+ * shared_stream != 0 is the demo's own schedule: ONE stream rng[0], restaurants visited in order, which
+ * reproduces the reference's draws uniform for uniform (the parity mode; serial by construction).
+ * t, T and rng are updated in place.  The table must have been made with S_UVTABLE; it is grown (up to its
+ * maximum size) to cover the counts before the launch.  Returns 0, or non-zero with stb_last_error() set.
+ */
+int stb_ti_gibbs(stable_t *sp, double bpar, size_t R, const uint32_t *tok_off, const uint32_t *tok_dish, const float *H,
+                 uint32_t D, const uint32_t *n, uint16_t *t, uint32_t *T, uint64_t *rng, int shared_stream, int sweeps);
+/* device milliseconds of the most recent stb_ti_gibbs kernel on this table */
+double stb_last_gibbs_ms(const stable_t *sp);
+
+/*
  * Per-chain replacement for the C library's rand() / srand() (glibc's additive feedback generator,
  * csrc/rand31.h): stb_rand31_seed(g, s) puts g in the state srand(s) puts the global generator in,
  * stb_rand31_next(g) returns what rand() would return next.  The batched ARS samplers draw each

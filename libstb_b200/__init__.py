@@ -81,6 +81,10 @@ def lib() -> C.CDLL:
     L.samplea2.argtypes = [d, vp, C.c_int, ip, u32p, C.POINTER(u32p), C.POINTER(C.POINTER(C.c_uint16)), vp, dp, vp,
                            C.c_int, C.c_int]
     L.logminus.restype, L.logminus.argtypes = d, [d, d]
+    L.stb_ti_gibbs.restype = C.c_int
+    L.stb_ti_gibbs.argtypes = [vp, d, C.c_size_t, u32p, u32p, C.POINTER(C.c_float), C.c_uint32, u32p,
+                               C.POINTER(C.c_uint16), u32p, C.POINTER(C.c_uint64), C.c_int, C.c_int]
+    L.stb_last_gibbs_ms.restype, L.stb_last_gibbs_ms.argtypes = d, [vp]
     L.stb_partition_sample.restype = C.c_int
     L.stb_partition_sample.argtypes = [vp, d, u32p, C.POINTER(C.c_uint16), dp, u32p, C.c_size_t,
                                        C.POINTER(C.c_uint16), C.c_size_t, C.c_int]
@@ -125,6 +129,8 @@ def lib() -> C.CDLL:
     L.stb_samplea_batch.restype = C.c_int
     L.stb_samplea_batch.argtypes = [dp, C.c_size_t, C.c_int, ip, u32p, C.POINTER(u32p),
                                     C.POINTER(C.POINTER(C.c_uint16)), dp, C.c_int, u64p, C.c_int, vp]
+    L.stb_samplea2_batch.restype = C.c_int
+    L.stb_samplea2_batch.argtypes = L.stb_samplea_batch.argtypes
     L.stb_sampleb_batch.restype = C.c_int
     L.stb_sampleb_batch.argtypes = [dp, C.c_size_t, C.c_int, d, d, u32p, u32p, dp, u64p, C.c_int, vp]
     L.stb_samplea_batch_multi.restype = C.c_int
@@ -231,6 +237,34 @@ class Table:
                                         m.ctypes.data_as(u16p), n_m, int(bool(exact))):
             raise RuntimeError("stb_partition_sample failed: " + self._L.stb_last_error().decode())
         return m[:n_m], off
+
+    def ti_gibbs(self, bpar, tok_off, tok_dish, H, n, t, T, rng, shared_stream=False, sweeps=1):
+        """stb_ti_gibbs: table-indicator Gibbs sweeps over R restaurants on the device (test/demo.c:405-434).
+        n, t: (R, D) counts / table counts, T: (R,) sums of t, tok_off: (R+1,) offsets into tok_dish,
+        rng: 48-bit stream states, one per restaurant (one in all with shared_stream).  Returns new (t, T, rng)."""
+        n = np.ascontiguousarray(n, dtype=np.uint32)
+        t = np.array(t, dtype=np.uint16, order="C")
+        T = np.array(T, dtype=np.uint32)
+        rng = np.array(rng, dtype=np.uint64)
+        tok_off = np.ascontiguousarray(tok_off, dtype=np.uint32)
+        tok_dish = np.ascontiguousarray(tok_dish, dtype=np.uint32)
+        H = np.ascontiguousarray(H, dtype=np.float32)
+        R, D = n.shape
+        if t.shape != (R, D) or T.shape != (R,) or tok_off.shape != (R + 1,) or H.shape != (D,):
+            raise ValueError("ti_gibbs: shapes")
+        if rng.shape[0] != (1 if shared_stream else R):
+            raise ValueError("ti_gibbs: one stream per restaurant (one in all with shared_stream)")
+        u32p = C.POINTER(C.c_uint32)
+        if self._L.stb_ti_gibbs(self.sp, float(bpar), R, tok_off.ctypes.data_as(u32p), tok_dish.ctypes.data_as(u32p),
+                                H.ctypes.data_as(C.POINTER(C.c_float)), D, n.ctypes.data_as(u32p),
+                                t.ctypes.data_as(C.POINTER(C.c_uint16)), T.ctypes.data_as(u32p),
+                                rng.ctypes.data_as(C.POINTER(C.c_uint64)), int(bool(shared_stream)), int(sweeps)):
+            raise RuntimeError("stb_ti_gibbs failed: " + self._L.stb_last_error().decode())
+        return t, T, rng
+
+    @property
+    def last_gibbs_ms(self):
+        return self._L.stb_last_gibbs_ms(self.sp)
 
     def rows(self, which_V, n0, nrows):
         """Rows n0..n0+nrows-1 as an (nrows, ld) float64 array; column j holds m=j+1."""
@@ -407,6 +441,22 @@ def samplea_batch(a, counts, bpar, rng, loops=1, bpar_per_chain=False, trace_cap
     rc = L.stb_samplea_batch(*args) if devices is False else L.stb_samplea_batch_multi(*_device_list(devices), *args)
     if rc:
         raise RuntimeError(f"stb_samplea_batch failed ({rc}): " + L.stb_last_error().decode())
+    return a, rng, {"evals": st.evals, "rounds": st.rounds, "eval_ms": st.eval_ms, "trace": keep}
+
+
+def samplea2_batch(a, counts, bpar, rng, loops=1, bpar_per_chain=False, trace_cap=0):
+    """stb_samplea2_batch: the table-free discount update (seat partitions against one table per chain, then one
+    slice step) for C chains; returns (a_new, rng_new, stats dict)."""
+    L = lib()
+    a = np.array(a, dtype=np.float64)
+    rng = np.array(rng, dtype=np.uint64)
+    bpar = np.ascontiguousarray(bpar, dtype=np.float64)
+    st, keep = _stats(a.shape[0], trace_cap)
+    dp, u64p = C.POINTER(C.c_double), C.POINTER(C.c_uint64)
+    rc = L.stb_samplea2_batch(a.ctypes.data_as(dp), a.shape[0], *counts.args(), bpar.ctypes.data_as(dp), int(bpar_per_chain),
+                              rng.ctypes.data_as(u64p), loops, C.byref(st))
+    if rc:
+        raise RuntimeError(f"stb_samplea2_batch failed ({rc}): " + L.stb_last_error().decode())
     return a, rng, {"evals": st.evals, "rounds": st.rounds, "eval_ms": st.eval_ms, "trace": keep}
 
 

@@ -103,12 +103,14 @@ __global__ void ti_gibbs_kernel(const T *__restrict__ tab, size_t ld, unsigned u
   rng[j] = r.x;
 }
 
-extern "C" int stb_cuda_ti_gibbs(stb_dev_t *d, const void *tabV, size_t ld, int is_float, int device, unsigned usedN,
-                                 unsigned usedM, double apar, double bpar, size_t R, const uint32_t *tok_off,
-                                 const uint32_t *tok_dish, const float *H, uint32_t D, const uint32_t *n, uint16_t *t,
-                                 uint32_t *T, uint64_t *rng, int shared_stream, int sweeps, float *ms) {
-  (void)d;
-  stb::DeviceGuard guard(device);
+extern "C" int stb_cuda_ti_gibbs(stb_dev_t *d, unsigned usedN, unsigned usedM, double apar, double bpar, size_t R,
+                                 const uint32_t *tok_off, const uint32_t *tok_dish, const float *H, uint32_t D,
+                                 const uint32_t *n, uint16_t *t, uint32_t *T, uint64_t *rng, int shared_stream, int sweeps,
+                                 float *ms) {
+  const void *tabV = stb_cuda_table_ptr(d, STB_TAB_V);
+  const size_t ld = stb_cuda_table_ld(d);
+  const int is_float = stb_cuda_table_is_float(d);
+  stb::DeviceGuard guard(stb_cuda_table_device(d));
   int rc = 0;
   const size_t ntok = tok_off[R], nstreams = shared_stream ? 1 : R;
   uint32_t *d_off = NULL, *d_dish = NULL, *d_n = NULL, *d_T = NULL;
@@ -119,6 +121,10 @@ extern "C" int stb_cuda_ti_gibbs(stb_dev_t *d, const void *tabV, size_t ld, int 
   if (guard.err != cudaSuccess) {
     stb_cuda_set_error("cudaSetDevice", (int)guard.err);
     return (int)guard.err;
+  }
+  if (!tabV) {
+    stb_cuda_set_error("stb_cuda_ti_gibbs: the table has no V slab", 0);
+    return -1;
   }
   GCK(cudaMalloc(&d_off, (R + 1) * sizeof(uint32_t)));
   GCK(cudaMalloc(&d_dish, (ntok ? ntok : 1) * sizeof(uint32_t)));

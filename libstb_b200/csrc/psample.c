@@ -218,6 +218,7 @@ double logminus(double x, double y) { /* log(e^x - e^y), lib/samplea.c:229-239 *
 }
 
 static int g_partition_mode = STB_PARTITION_REFERENCE;
+int stb_get_partition_mode(void) { return g_partition_mode; }
 int stb_set_partition_mode(int mode) {
   const int was = g_partition_mode;
   if (mode == STB_PARTITION_REFERENCE || mode == STB_PARTITION_EXACT) g_partition_mode = mode;

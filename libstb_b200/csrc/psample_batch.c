@@ -1028,3 +1028,135 @@ done:
   free(d.arg);
   return rc;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* samplea2 for C chains (stb_samplea2_batch)                                                  */
+/* ------------------------------------------------------------------------------------------ */
+/*
+ * Chain c updates its discount a[c] the table-free way (lib/samplea.c:227-341): its own Stirling table at a[c]
+ * (one table per chain out of a discount sweep -- the scalar samplea2 is handed the caller's table), the
+ * partition step of every node with 1 < t < n against it on the device, the chain's uniforms taken from its
+ * stream rng[c] in the order the scalar call takes them (stb_cuda_sweep_partition), then ONE slice / ARS step
+ * for all chains in lock-step.  The sampled sizes of a chain are kept as a histogram of the likelihood's
+ * arguments j = size - 1 (that is all the likelihood needs), so an evaluation is a device reduction over at most
+ * max n bins in a fixed order, next to the same lgamma reduction over the restaurants samplea's batch uses.
+ */
+typedef struct {
+  stb_sweep_t *sweep;
+  stb_pstat_dev_t *ps;
+  int bpar_per_chain;
+  double *lg, *hs;
+  stb_sample_stats *st;
+} PartitionBatchPost;
+
+static int partition_post_device(void *ctx, const double *x, const int *chain, size_t cnt, double *out) {
+  PartitionBatchPost *d = (PartitionBatchPost *)ctx;
+  float ms = 0.f;
+  size_t j;
+  for (j = 0; j < cnt; j++)
+    if (!(x[j] > 0)) {
+      fprintf(stderr, "samplea2: the sampler proposed a discount <= 0\n");
+      return 1;
+    }
+  if (stb_cuda_pstat_aterms_lg(d->ps, x, chain, cnt, d->bpar_per_chain, d->lg, &ms)) return 1;
+  if (d->st) d->st->eval_ms += ms;
+  if (stb_sweep_hist_eval(d->sweep, x, chain, cnt, d->hs, &ms)) return 1;
+  if (d->st) d->st->eval_ms += ms;
+  for (j = 0; j < cnt; j++) out[j] = d->lg[j] + d->hs[j];
+  return 0;
+}
+
+int stb_discount_step_partition_batch(double *a, size_t C, int I, const int *K, const scnt_int *T, scnt_int **n,
+                                      stcnt_int **t, const double *bpar, int bpar_per_chain, uint64_t *rng,
+                                      const stb_ars_source *ars, int loops, int exact, stb_sample_stats *st,
+                                      double *partition_ms) {
+  size_t nodes = 0, draws = 0, j = 0, c;
+  uint32_t *pn = NULL, *pdraw = NULL, *hbase = NULL;
+  uint16_t *pt = NULL;
+  double *lo = NULL, *hi = NULL;
+  unsigned maxn = 1, maxt = 1, Nx, Mx, hbins;
+  PartitionBatchPost d;
+  float ms = 0.f;
+  int i, k, rc = -1;
+  memset(&d, 0, sizeof d);
+  if (partition_ms) *partition_ms = 0;
+  if (!C) return 0;
+  for (i = 0; i < I; i++)
+    for (k = 0; k < K[i]; k++) {
+      if (n[i][k] > maxn) maxn = n[i][k];
+      if (t[i][k] > maxt) maxt = t[i][k];
+      if (t[i][k] > 1 && t[i][k] < n[i][k]) nodes++;
+    }
+  Mx = maxt < 10 ? 10u : maxt; /* the clamps S_make applies (lib/stable.c:118-129) */
+  Nx = maxn < Mx ? Mx : maxn;
+  hbins = maxn + 1;
+  pn = (uint32_t *)malloc(sizeof(uint32_t) * (nodes ? nodes : 1));
+  pdraw = (uint32_t *)malloc(sizeof(uint32_t) * (nodes ? nodes : 1));
+  pt = (uint16_t *)malloc(sizeof(uint16_t) * (nodes ? nodes : 1));
+  hbase = (uint32_t *)calloc(hbins, sizeof(uint32_t));
+  lo = (double *)malloc(sizeof(double) * C);
+  hi = (double *)malloc(sizeof(double) * C);
+  if (!pn || !pdraw || !pt || !hbase || !lo || !hi) goto done;
+  /* the uniforms come off a chain's stream in (i,k) order: one per node (:293), or one per round in the exact mode;
+   * a node with one table puts n - 1 into every chain's argument list (:115-143) */
+  for (i = 0; i < I; i++)
+    for (k = 0; k < K[i]; k++) {
+      const scnt_int nk = n[i][k];
+      const stcnt_int tk = t[i][k];
+      if (tk > 1 && tk < nk) {
+        pn[j] = nk;
+        pt[j] = tk;
+        pdraw[j] = (uint32_t)draws;
+        draws += exact ? (size_t)tk - 1 : 1;
+        j++;
+      } else if (nk != 0 && tk == 1 && nk > 1)
+        hbase[nk - 1]++;
+    }
+  for (c = 0; c < C; c++) discount_bracket(a[c], ars != NULL, &lo[c], &hi[c]);
+  d.sweep = sweep_acquire(Nx, Mx);
+  if (!d.sweep || stb_sweep_set_nodes(d.sweep, pn, pt, pdraw, nodes, hbase, hbins)) goto done;
+  if (stb_sweep_partition(d.sweep, a, C, rng, exact, NULL, &ms)) {
+    fprintf(stderr, "samplea2: partition sampling failed: %s\n", stb_last_error());
+    goto done;
+  }
+  if (partition_ms) *partition_ms = ms;
+  if (st) st->eval_ms += ms;
+  for (c = 0; c < C; c++) rng[c] = stb_cuda_lcg48_jump(rng[c], draws);
+  {
+    const size_t slots = C * 5 + 64; /* a round evaluates at most depth + 1 = 5 points per chain */
+    d.lg = (double *)malloc(sizeof(double) * slots);
+    d.hs = (double *)malloc(sizeof(double) * slots);
+    if (!d.lg || !d.hs) goto done;
+    d.ps = stb_cuda_pstat_create(I, T, NULL, bpar, bpar_per_chain ? C * (size_t)I : (size_t)I, slots);
+    if (!d.ps) goto done;
+  }
+  d.bpar_per_chain = bpar_per_chain;
+  d.st = st;
+  if (ars) {
+    rc = stb_ars_lockstep(a, C, lo, hi, ars, partition_post_device, &d, st, NULL);
+    for (c = 0; rc == 0 && c < C; c++)
+      if (a[c] < lo[c] || a[c] > hi[c]) {
+        fprintf(stderr, "samplea2: arms_simple left [%lg, %lg] (chain %zu)\n", lo[c], hi[c], c);
+        rc = 1 + (int)c;
+      }
+  } else
+    rc = stb_slice_lockstep(a, C, lo, hi, rng, loops, partition_post_device, &d, st, 4, 0);
+done:
+  if (d.sweep) sweep_release(d.sweep, Nx, Mx);
+  if (d.ps) stb_cuda_pstat_destroy(d.ps);
+  free(pn);
+  free(pdraw);
+  free(pt);
+  free(hbase);
+  free(lo);
+  free(hi);
+  free(d.lg);
+  free(d.hs);
+  return rc;
+}
+
+int stb_samplea2_batch(double *a, size_t C, int I, const int *K, const scnt_int *T, scnt_int **n, stcnt_int **t,
+                       const double *bpar, int bpar_per_chain, uint64_t *rng, int loops, stb_sample_stats *st) {
+  return stb_discount_step_partition_batch(a, C, I, K, T, n, t, bpar, bpar_per_chain, rng, NULL, loops,
+                                           stb_get_partition_mode() == STB_PARTITION_EXACT, st, NULL);
+}

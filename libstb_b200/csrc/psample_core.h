@@ -53,5 +53,19 @@ int stb_concentration_step(double *b, size_t C, int I, double shape, double scal
 int stb_discount_step_partition(double *a, stable_t *S, int I, const int *K, const scnt_int *T, scnt_int **n, stcnt_int **t,
                                 const double *bpar, uint64_t *rng, const stb_ars_source *ars, int loops, int exact,
                                 int verbose);
+/* the same for C chains, every chain against its own table out of a discount sweep (device back end);
+ * *partition_ms (may be NULL): device time of the fills and the partition kernels */
+int stb_discount_step_partition_batch(double *a, size_t C, int I, const int *K, const scnt_int *T, scnt_int **n,
+                                      stcnt_int **t, const double *bpar, int bpar_per_chain, uint64_t *rng,
+                                      const stb_ars_source *ars, int loops, int exact, stb_sample_stats *st,
+                                      double *partition_ms);
+int stb_get_partition_mode(void);
+
+/* device steps of the batched partition update on a sweep handle (stable.c -> stb_cuda.cu) */
+int stb_sweep_set_nodes(stb_sweep_t *w, const uint32_t *n, const uint16_t *t, const uint32_t *draw, size_t count,
+                        const uint32_t *hbase, unsigned hbins);
+int stb_sweep_partition(stb_sweep_t *w, const double *a, size_t na, const uint64_t *x0, int exact, uint32_t *hist_out,
+                        float *ms);
+int stb_sweep_hist_eval(stb_sweep_t *w, const double *x, const int *chain, size_t cnt, double *out, float *ms);
 
 #endif

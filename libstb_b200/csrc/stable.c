@@ -55,6 +55,7 @@ struct stb_table_impl {
    * refreshed from it on first use after a fill, not by every fill: callers that only do batched
    * look-ups (samplea) never pay for the copy. */
   int s1_stale;
+  float last_gibbs_ms; /* device time of the most recent stb_ti_gibbs kernel */
 };
 
 static void lock(stable_t *sp) { /* exclusive: growth, refill */
@@ -576,6 +577,68 @@ int stb_partition_sample(stable_t *sp, double a, const uint32_t *n, const uint16
   }
 }
 
+/*
+ * Table-indicator Gibbs sweeps on the device (stb_b200.h; the per-token update of test/demo.c:405-434).
+ * The table is grown first to cover every (n, t+1) a sweep can look up, so that the kernel never needs the host.
+ */
+int stb_ti_gibbs(stable_t *sp, double bpar, size_t R, const uint32_t *tok_off, const uint32_t *tok_dish, const float *H,
+                 uint32_t D, const uint32_t *n, uint16_t *t, uint32_t *T, uint64_t *rng, int shared_stream, int sweeps) {
+  unsigned maxn = 0;
+  size_t j, c;
+  uint32_t i;
+  if (!sp || !sp->impl || !(sp->flags & S_UVTABLE)) {
+    stb_cuda_set_error("stb_ti_gibbs: the table has no V (make it with S_UVTABLE)", 0);
+    return 1;
+  }
+  if (!R || sweeps < 1) return 0;
+  for (j = 0; j < R; j++) {
+    uint32_t Tj = 0;
+    if (tok_off[j + 1] < tok_off[j]) {
+      stb_cuda_set_error("stb_ti_gibbs: token offsets must not decrease", 0);
+      return 1;
+    }
+    for (i = 0; i < D; i++) {
+      const uint32_t nn = n[j * (size_t)D + i], tt = t[j * (size_t)D + i];
+      if (tt > nn || (nn > 0 && tt == 0)) {
+        stb_cuda_set_error("stb_ti_gibbs: counts need 1 <= t <= n wherever n > 0", 0);
+        return 1;
+      }
+      if (nn > maxn) maxn = nn;
+      Tj += tt;
+    }
+    if (Tj != T[j]) {
+      stb_cuda_set_error("stb_ti_gibbs: T[j] is not the sum of t[j][.]", 0);
+      return 1;
+    }
+    for (c = tok_off[j]; c < tok_off[j + 1]; c++)
+      if (tok_dish[c] >= D || n[j * (size_t)D + tok_dish[c]] == 0) {
+        stb_cuda_set_error("stb_ti_gibbs: a token names a dish the restaurant does not serve", 0);
+        return 1;
+      }
+  }
+  /* a look-up is V(n, t+1) with t+1 <= n: rows up to max n, columns up to min(max n, maxM) */
+  if (maxn > sp->maxN) {
+    stb_cuda_set_error("stb_ti_gibbs: counts beyond the table's maximum size", 0);
+    return 1;
+  }
+  {
+    unsigned wantM = maxn < sp->maxM ? maxn : sp->maxM;
+    if (maxn > sp->usedN || wantM > sp->usedM)
+      if (extend(sp, maxn > sp->usedN ? maxn : sp->usedN, wantM > sp->usedM ? wantM : sp->usedM)) return 1;
+  }
+  {
+    int rc;
+    float ms = 0;
+    lock(sp);
+    rc = stb_cuda_ti_gibbs(sp->impl->dev, sp->usedN, sp->usedM, sp->a, bpar, R, tok_off, tok_dish, H, D, n, t, T, rng,
+                           shared_stream, sweeps, &ms);
+    sp->impl->last_gibbs_ms = ms;
+    unlock(sp);
+    return rc;
+  }
+}
+double stb_last_gibbs_ms(const stable_t *sp) { return sp && sp->impl ? sp->impl->last_gibbs_ms : 0; }
+
 /* ------------------------------------------------------------------------------------------ */
 /* discount sweep (stb_b200.h)                                                                 */
 /* ------------------------------------------------------------------------------------------ */
@@ -600,6 +663,18 @@ int stb_sweep_set_pairs(stb_sweep_t *w, const uint32_t *n, const uint32_t *m, si
 int stb_sweep_run(stb_sweep_t *w, const double *a, size_t na, double *gather_out, double *sum_out,
                   double *lastrow_out) {
   return w ? stb_cuda_sweep_run(w->dev, a, na, gather_out, sum_out, lastrow_out, &w->last_ms) : 1;
+}
+/* the batched partition step of samplea2 (psample_batch.c; declared in psample_core.h) */
+int stb_sweep_set_nodes(stb_sweep_t *w, const uint32_t *n, const uint16_t *t, const uint32_t *draw, size_t count,
+                        const uint32_t *hbase, unsigned hbins) {
+  return w ? stb_cuda_sweep_set_nodes(w->dev, n, t, draw, count, hbase, hbins) : 1;
+}
+int stb_sweep_partition(stb_sweep_t *w, const double *a, size_t na, const uint64_t *x0, int exact, uint32_t *hist_out,
+                        float *ms) {
+  return w ? stb_cuda_sweep_partition(w->dev, a, na, x0, exact, hist_out, ms) : 1;
+}
+int stb_sweep_hist_eval(stb_sweep_t *w, const double *x, const int *chain, size_t cnt, double *out, float *ms) {
+  return w ? stb_cuda_sweep_hist_eval(w->dev, x, chain, cnt, out, ms) : 1;
 }
 double stb_sweep_last_fill_ms(const stb_sweep_t *w) { return w->last_ms; }
 int stb_sweep_tables_in_flight(const stb_sweep_t *w) { return stb_cuda_sweep_tables_in_flight(w->dev); }

@@ -134,6 +134,9 @@ extern "C" void stb_cuda_table_destroy(stb_dev_t *d) {
   free(d);
 }
 
+extern "C" int stb_cuda_table_device(const stb_dev_t *d) { return d->device; }
+extern "C" int stb_cuda_table_is_float(const stb_dev_t *d) { return d->is_float; }
+
 static size_t elem_size(const stb_dev_t *d) { return d->is_float ? sizeof(float) : sizeof(double); }
 
 extern "C" size_t stb_cuda_table_ld(const stb_dev_t *d) { return d->ld; }
@@ -630,6 +633,17 @@ struct stb_sweep_dev {
   double *h_stage;     // pinned staging for the sums of a whole run
   int *h_flags;        // pinned: watchdog flag of every wave of a run
   size_t stage_cap, flags_cap;
+  // the batched seat-partition step of samplea2 (stb_cuda_sweep_set_nodes / _partition / _hist_eval)
+  uint32_t *d_pn, *d_pdraw, *d_porder;  // [pcount]: customers, first draw index, nodes longest first
+  uint16_t *d_pt;                       // [pcount]: tables
+  size_t pcount, pnodes_cap;
+  unsigned hbins;                       // histogram bins per chain: arguments j = size - 1 = 0 .. hbins-1
+  uint32_t *d_hist, *d_hbase;           // [hist_cap][hbins] per-chain histograms of the sampled sizes; [hbins] what every chain starts from
+  size_t hist_cap;
+  unsigned long long *d_x0;             // [slabs] stream states of a wave's chains
+  double *d_ex, *d_eout;                // evaluation points / results
+  int *d_echain;
+  size_t eval_cap;
 };
 
 /* S_S conventions (lib/stable.c:941-949) on a dense slab; partial sums per block in a fixed order */
@@ -763,6 +777,16 @@ extern "C" void stb_cuda_sweep_destroy(stb_sweep_dev_t *w) {
   cudaFree(w->d_sum);
   if (w->h_stage) cudaFreeHost(w->h_stage);
   if (w->h_flags) cudaFreeHost(w->h_flags);
+  cudaFree(w->d_pn);
+  cudaFree(w->d_pdraw);
+  cudaFree(w->d_porder);
+  cudaFree(w->d_pt);
+  cudaFree(w->d_hist);
+  cudaFree(w->d_hbase);
+  cudaFree(w->d_x0);
+  cudaFree(w->d_ex);
+  cudaFree(w->d_eout);
+  cudaFree(w->d_echain);
   stb::strip_state_free(&w->strip);
   if (w->ev0) cudaEventDestroy(w->ev0);
   if (w->ev1) cudaEventDestroy(w->ev1);
@@ -1033,4 +1057,318 @@ extern "C" void *stb_cuda_host_alloc(size_t bytes) {
 
 extern "C" void stb_cuda_host_free(void *p) {
   if (p) cudaFreeHost(p);
+}
+
+// ---------------------------------------------------------------------------------------------
+// samplea2 over many chains: the seat-partition step against one table per chain (lib/samplea.c:290-321)
+// ---------------------------------------------------------------------------------------------
+/* glibc's 48-bit generator k steps on: X -> A^k X + C (A^k - 1)/(A - 1) mod 2^48 by repeated squaring */
+__host__ __device__ static inline unsigned long long lcg48_jump(unsigned long long x, unsigned long long k) {
+  unsigned long long am = 1, ap = 0, cm = 0x5DEECE66DULL, cp = 0xBULL;
+  while (k) {
+    if (k & 1) {
+      am = am * cm;
+      ap = ap * cm + cp;
+    }
+    cp = (cm + 1) * cp;
+    cm = cm * cm;
+    k >>= 1;
+  }
+  return (am * x + ap) & 0xFFFFFFFFFFFFULL;
+}
+extern "C" uint64_t stb_cuda_lcg48_jump(uint64_t x, uint64_t k) { return lcg48_jump(x, k); }
+
+/*
+ * partition_kernel's walk for the nodes of MANY chains at once: blockIdx.y is the chain's table of the wave
+ * (its slab, its discount, its stream), the sizes go into the chain's histogram of likelihood arguments
+ * j = size - 1 (integer counts: the order the threads arrive in does not matter) instead of a list, and the
+ * log-uniforms are made here -- the chain's stream is glibc's 48-bit generator, draw number q is the state
+ * q + 1 steps on, reached by a jump and then stepped round by round.  (log is CUDA's here and glibc's in the
+ * scalar samplea2: a walk would have to stop within an ulp of a log-uniform for the two to differ.)
+ */
+template <typename T>
+__global__ void partition_hist_kernel(const T *__restrict__ slabs, const double *__restrict__ s1s, size_t slab_elems, size_t ld,
+                                      unsigned Nrows, const stb::StripTable *__restrict__ tables,
+                                      const unsigned long long *__restrict__ x0, const uint32_t *__restrict__ n,
+                                      const uint16_t *__restrict__ t, const uint32_t *__restrict__ draw,
+                                      const uint32_t *__restrict__ order, size_t count, int exact, uint32_t *__restrict__ hist,
+                                      unsigned hbins) {
+  const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= count) return;
+  const int tb = blockIdx.y;
+  const T *tab = slabs + (size_t)tb * slab_elems;
+  const double *s1 = s1s + (size_t)tb * Nrows;
+  const double a = tables[tb].a;
+  uint32_t *h = hist + (size_t)tb * hbins;
+  const size_t i = order[slot];
+  int N = (int)n[i];
+  const int t0 = (int)t[i];
+  auto S = [&](int nn, int mm) -> double {
+    if (nn == mm) return 0.0;
+    if (mm == 1) return s1[nn - 1];
+    return (double)tab[(size_t)(nn - 1) * ld + (mm - 1)];
+  };
+  unsigned long long xs = lcg48_jump(x0[tb], (unsigned long long)draw[i] + 1);
+  auto logu = [&]() -> double { return log((double)xs * (1.0 / 281474976710656.0)); };
+  double ptot = S(N, t0);
+  double rem = exact ? logu() : __dadd_rn(ptot, logu());
+  const double shift = exact ? 1.0 : 0.0;
+  int M = t0 - 1, l = 1;
+  double fact = 0.0;
+  double s_next = S(N - 1, M);
+  while (M >= 1) {
+    const double s_cur = s_next;
+    s_next = S(N - (l + 1 <= N - M ? l + 1 : l), M);
+    if (l > 1)
+      fact = __dadd_rn(fact, log(__ddiv_rn(__dmul_rn(__dsub_rn((double)l - shift, a), (double)(N - l + 1)),
+                                           (double)(l - 1))));
+    const double term = __dsub_rn(__dadd_rn(fact, s_cur), ptot);
+    bool done = term >= rem;
+    if (!done) {
+      rem = logminus_dev(rem, term);
+      l++;
+      if (l > N - M) {
+        l = N - M;
+        done = true;
+      }
+    }
+    if (done) {
+      if (l > 1) atomicAdd(&h[l - 1], 1u);
+      N -= l;
+      M--;
+      l = 1;
+      fact = 0.0;
+      if (M >= 1) {
+        s_next = S(N - 1, M);
+        if (exact) {
+          ptot = S(N, M + 1);
+          xs = (0x5DEECE66DULL * xs + 0xBULL) & 0xFFFFFFFFFFFFULL;
+          rem = logu();
+        }
+      }
+    }
+  }
+  if (N > 1) atomicAdd(&h[N - 1], 1u);  // what is left of the node's customers sits at its last table
+}
+
+__global__ void hist_init_kernel(uint32_t *__restrict__ hist, const uint32_t *__restrict__ base, unsigned hbins, size_t rows) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows * hbins) hist[i] = base[i % hbins];
+}
+
+/* sum_j hist[chain][j] (lgamma(j + 1 - x) - lgamma(1 - x)): one block per point, partial sums in a fixed order */
+__global__ void hist_eval_kernel(const uint32_t *__restrict__ hist, unsigned hbins, const double *__restrict__ x,
+                                 const int *__restrict__ chain, double *__restrict__ out) {
+  __shared__ double red[256];
+  const size_t e = blockIdx.x;
+  const double xv = x[e];
+  const uint32_t *h = hist + (size_t)chain[e] * hbins;
+  const double lg1 = lgamma(1.0 - xv);
+  double acc = 0.0;
+  for (unsigned j = 1 + threadIdx.x; j < hbins; j += blockDim.x) {
+    const uint32_t c = h[j];
+    if (c) acc += (double)c * (lgamma((double)j + 1.0 - xv) - lg1);
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[e] = red[0];
+}
+
+/*
+ * The nodes of a statistics set that take part in the partition step (1 < t < n), in the order their uniforms
+ * come off a chain's stream; draw[j]: the number of the node's first draw (reference mode: j; exact mode: the
+ * t - 1 draws of the nodes before it); hbase[hbins]: the arguments every chain's histogram starts from (the nodes
+ * with one table).  Sorted longest first here, like stb_cuda_partition.
+ */
+extern "C" int stb_cuda_sweep_set_nodes(stb_sweep_dev_t *w, const uint32_t *n, const uint16_t *t, const uint32_t *draw,
+                                        size_t count, const uint32_t *hbase, unsigned hbins) {
+  ON_DEVICE(w->device);
+  std::vector<uint32_t> order, start;
+  try {
+    order.resize(count ? count : 1);
+    start.assign((size_t)w->N + 2, 0);
+  } catch (...) {
+    snprintf(g_err, sizeof g_err, "stb_cuda_sweep_set_nodes: out of host memory");
+    return -1;
+  }
+  for (size_t i = 0; i < count; i++) {
+    if (n[i] > w->N || t[i] > w->M || t[i] < 2 || t[i] >= n[i]) {
+      snprintf(g_err, sizeof g_err, "stb_cuda_sweep_set_nodes: node %zu (n=%u, t=%u) outside the tables or not 1 < t < n", i,
+               n[i], (unsigned)t[i]);
+      return -1;
+    }
+    start[w->N - n[i] + 1]++;
+  }
+  for (size_t v = 1; v < start.size(); v++) start[v] += start[v - 1];
+  for (size_t i = 0; i < count; i++) order[start[w->N - n[i]]++] = (uint32_t)i;
+  if (count > w->pnodes_cap) {
+    cudaFree(w->d_pn);
+    cudaFree(w->d_pdraw);
+    cudaFree(w->d_porder);
+    cudaFree(w->d_pt);
+    w->d_pn = w->d_pdraw = w->d_porder = NULL;
+    w->d_pt = NULL;
+    w->pnodes_cap = 0;
+    CK(cudaMalloc(&w->d_pn, count * sizeof(uint32_t)));
+    CK(cudaMalloc(&w->d_pdraw, count * sizeof(uint32_t)));
+    CK(cudaMalloc(&w->d_porder, count * sizeof(uint32_t)));
+    CK(cudaMalloc(&w->d_pt, count * sizeof(uint16_t)));
+    w->pnodes_cap = count;
+  }
+  if (hbins != w->hbins || !w->d_hbase) {
+    cudaFree(w->d_hbase);
+    cudaFree(w->d_hist);
+    w->d_hbase = w->d_hist = NULL;
+    w->hist_cap = 0;
+    w->hbins = 0;
+    CK(cudaMalloc(&w->d_hbase, (size_t)(hbins ? hbins : 1) * sizeof(uint32_t)));
+    w->hbins = hbins;
+  }
+  if (!w->d_x0) CK(cudaMalloc(&w->d_x0, (size_t)w->slabs * sizeof(unsigned long long)));
+  w->pcount = count;
+  if (count) {
+    CK(cudaMemcpyAsync(w->d_pn, n, count * sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
+    CK(cudaMemcpyAsync(w->d_pdraw, draw, count * sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
+    CK(cudaMemcpyAsync(w->d_porder, order.data(), count * sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
+    CK(cudaMemcpyAsync(w->d_pt, t, count * sizeof(uint16_t), cudaMemcpyHostToDevice, w->stream));
+  }
+  CK(cudaMemcpyAsync(w->d_hbase, hbase, (size_t)hbins * sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
+  CK(cudaStreamSynchronize(w->stream));
+  return 0;
+}
+
+/*
+ * One table per chain at its discount a[c] (waves of the sweep's resident slabs), the partition step of every
+ * node against it, chain c drawing from the stream state x0[c].  The histograms stay on the device for
+ * stb_cuda_sweep_hist_eval; hist_out (host, [na][hbins], may be NULL) receives a copy.  *ms: device time.
+ */
+extern "C" int stb_cuda_sweep_partition(stb_sweep_dev_t *w, const double *a, size_t na, const uint64_t *x0, int exact,
+                                        uint32_t *hist_out, float *ms) {
+  ON_DEVICE(w->device);
+  const size_t es = w->is_float ? 4 : 8;
+  const size_t slab_elems = (size_t)w->N * w->ld;
+  if (ms) *ms = 0.f;
+  if (!na) return 0;
+  if (!w->d_hbase || !w->hbins) {
+    snprintf(g_err, sizeof g_err, "stb_cuda_sweep_partition: no nodes set");
+    return -1;
+  }
+  if (na > w->hist_cap) {
+    cudaFree(w->d_hist);
+    w->d_hist = NULL;
+    w->hist_cap = 0;
+    CK(cudaMalloc(&w->d_hist, na * (size_t)w->hbins * sizeof(uint32_t)));
+    w->hist_cap = na;
+  }
+  const size_t chunk = (size_t)w->slabs;
+  const size_t nwaves = (na + chunk - 1) / chunk;
+  if (nwaves > w->flags_cap) {
+    if (w->h_flags) cudaFreeHost(w->h_flags);
+    w->h_flags = NULL;
+    w->flags_cap = 0;
+    CK(cudaHostAlloc(&w->h_flags, nwaves * sizeof(int), cudaHostAllocDefault));
+    w->flags_cap = nwaves;
+  }
+  memset(w->h_flags, 0, nwaves * sizeof(int));
+  std::vector<stb::StripTable> tabs(chunk);
+  CK(cudaEventRecord(w->ev0, w->stream));
+  {
+    const size_t tot = na * (size_t)w->hbins;
+    hist_init_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, w->stream>>>(w->d_hist, w->d_hbase, w->hbins, na);
+    CK(cudaGetLastError());
+  }
+  cudaEvent_t ev_fill_end = w->ev1;
+  size_t wave = 0;
+  for (size_t j0 = 0; j0 < na; j0 += chunk, ++wave) {
+    const int nt = (int)((na - j0 < chunk) ? na - j0 : chunk);
+    for (int t = 0; t < nt; t++) {
+      tabs[t].tabS = (char *)w->slab + (size_t)t * slab_elems * es;
+      tabs[t].tabV = NULL;
+      tabs[t].s1 = w->s1 + (size_t)t * w->N;
+      tabs[t].a = a[j0 + t];
+    }
+    stb::StripFillArgs args;
+    args.tables = tabs.data();
+    args.ntables = nt;
+    args.has_S = 1;
+    args.has_V = 0;
+    args.is_float = w->is_float;
+    args.ld = w->ld;
+    args.N = w->N;
+    args.M = w->M;
+    args.num_sms = w->num_sms;
+    args.async_flag = w->h_flags + wave;
+    int rc = stb::strip_fill(&w->strip, args, w->stream, ev_fill_end, g_err, sizeof g_err);
+    if (rc) return rc;
+    if (w->pcount) {
+      CK(cudaMemcpyAsync(w->d_x0, x0 + j0, (size_t)nt * sizeof(unsigned long long), cudaMemcpyHostToDevice, w->stream));
+      dim3 grid((unsigned)((w->pcount + 63) / 64), (unsigned)nt);
+      uint32_t *hist = w->d_hist + j0 * (size_t)w->hbins;
+      if (w->is_float)
+        partition_hist_kernel<float><<<grid, 64, 0, w->stream>>>((const float *)w->slab, w->s1, slab_elems, w->ld, w->N,
+                                                                  w->strip.tables, w->d_x0, w->d_pn, w->d_pt, w->d_pdraw,
+                                                                  w->d_porder, w->pcount, exact, hist, w->hbins);
+      else
+        partition_hist_kernel<double><<<grid, 64, 0, w->stream>>>((const double *)w->slab, w->s1, slab_elems, w->ld, w->N,
+                                                                   w->strip.tables, w->d_x0, w->d_pn, w->d_pt, w->d_pdraw,
+                                                                   w->d_porder, w->pcount, exact, hist, w->hbins);
+      CK(cudaGetLastError());
+    }
+    // (the next wave's table list overwrites strip.tables: stream order keeps it behind this wave's kernel;
+    // the host copy `tabs` is consumed by strip_fill's cudaMemcpyAsync from pageable memory before it returns)
+  }
+  CK(cudaEventRecord(w->ev1, w->stream));
+  if (hist_out)
+    CK(cudaMemcpyAsync(hist_out, w->d_hist, na * (size_t)w->hbins * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+  CK(cudaStreamSynchronize(w->stream));
+  for (size_t v = 0; v < nwaves; v++)
+    if (w->h_flags[v]) {
+      snprintf(g_err, sizeof g_err, "stb_cuda_sweep_partition: pipeline watchdog fired in wave %zu", v);
+      return -2;
+    }
+  if (ms) CK(cudaEventElapsedTime(ms, w->ev0, w->ev1));
+  return 0;
+}
+
+/* out[e] = sum_j hist[chain[e]][j] (lgamma(j + 1 - x[e]) - lgamma(1 - x[e])) over the histograms of the last partition */
+extern "C" int stb_cuda_sweep_hist_eval(stb_sweep_dev_t *w, const double *x, const int *chain, size_t cnt, double *out,
+                                        float *ms) {
+  ON_DEVICE(w->device);
+  if (ms) *ms = 0.f;
+  if (!cnt) return 0;
+  if (!w->d_hist) {
+    snprintf(g_err, sizeof g_err, "stb_cuda_sweep_hist_eval: no histograms");
+    return -1;
+  }
+  for (size_t e = 0; e < cnt; e++)
+    if (chain[e] < 0 || (size_t)chain[e] >= w->hist_cap) {
+      snprintf(g_err, sizeof g_err, "stb_cuda_sweep_hist_eval: chain index out of range");
+      return -1;
+    }
+  if (cnt > w->eval_cap) {
+    cudaFree(w->d_ex);
+    cudaFree(w->d_eout);
+    cudaFree(w->d_echain);
+    w->d_ex = w->d_eout = NULL;
+    w->d_echain = NULL;
+    w->eval_cap = 0;
+    CK(cudaMalloc(&w->d_ex, cnt * sizeof(double)));
+    CK(cudaMalloc(&w->d_eout, cnt * sizeof(double)));
+    CK(cudaMalloc(&w->d_echain, cnt * sizeof(int)));
+    w->eval_cap = cnt;
+  }
+  CK(cudaMemcpyAsync(w->d_ex, x, cnt * sizeof(double), cudaMemcpyHostToDevice, w->stream));
+  CK(cudaMemcpyAsync(w->d_echain, chain, cnt * sizeof(int), cudaMemcpyHostToDevice, w->stream));
+  CK(cudaEventRecord(w->ev0, w->stream));
+  hist_eval_kernel<<<(unsigned)cnt, 256, 0, w->stream>>>(w->d_hist, w->hbins, w->d_ex, w->d_echain, w->d_eout);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(w->ev1, w->stream));
+  CK(cudaMemcpyAsync(out, w->d_eout, cnt * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
+  CK(cudaStreamSynchronize(w->stream));
+  if (ms) CK(cudaEventElapsedTime(ms, w->ev0, w->ev1));
+  return 0;
 }

@@ -127,6 +127,14 @@ int stb_cuda_sweep_run_dealt(stb_sweep_dev_t *w, const double *a, size_t na, siz
                              double *gather_out, double *sum_out, double *lastrow_out, float *fill_ms);
 /* tables one launch fills side by side for this extent on this device */
 int stb_cuda_sweep_tables_in_flight(const stb_sweep_dev_t *w);
+/* samplea2 over many chains (stb_cuda.cu): nodes of the partition step, the step itself against one table per
+ * chain, and the evaluation of the likelihood's table terms from the per-chain histograms of sampled sizes */
+int stb_cuda_sweep_set_nodes(stb_sweep_dev_t *w, const uint32_t *n, const uint16_t *t, const uint32_t *draw, size_t count,
+                             const uint32_t *hbase, unsigned hbins);
+int stb_cuda_sweep_partition(stb_sweep_dev_t *w, const double *a, size_t na, const uint64_t *x0, int exact,
+                             uint32_t *hist_out, float *ms);
+int stb_cuda_sweep_hist_eval(stb_sweep_dev_t *w, const double *x, const int *chain, size_t cnt, double *out, float *ms);
+uint64_t stb_cuda_lcg48_jump(uint64_t x, uint64_t k);
 
 /*
  * Per-restaurant statistics on the device and the I-term reductions of the batched samplers
@@ -149,6 +157,17 @@ int stb_cuda_pstat_bterms(stb_pstat_dev_t *p, const double *x, const double *Q, 
 int stb_cuda_pstat_betaQ(stb_pstat_dev_t *p, const double *b_in, uint64_t *rng, size_t C, double scale, double *Q,
                          float *ms);
 void stb_cuda_set_error(const char *what, int code);
+
+/*
+ * Table-indicator Gibbs sweeps over R restaurants reading V^n_m from the device table (gibbs_cuda.cu; the
+ * per-token update of test/demo.c:405-434).  Host arrays in, t / T / rng updated in place; *ms = device time
+ * of the kernel.  Returns 0 or an error code (text in stb_cuda_last_error()).
+ */
+int stb_cuda_ti_gibbs(stb_dev_t *d, unsigned usedN, unsigned usedM, double apar, double bpar, size_t R,
+                      const uint32_t *tok_off, const uint32_t *tok_dish, const float *H, uint32_t D, const uint32_t *n,
+                      uint16_t *t, uint32_t *T, uint64_t *rng, int shared_stream, int sweeps, float *ms);
+int stb_cuda_table_device(const stb_dev_t *d);
+int stb_cuda_table_is_float(const stb_dev_t *d);
 
 /* raw device pointer of a table (for the batched samplers and for tests) */
 void *stb_cuda_table_ptr(stb_dev_t *d, int which);

@@ -242,3 +242,62 @@ double orc_partition_logp(const orc_table *tb, double a, unsigned N, unsigned M,
   for (j = 2; j <= l; j++) fact += log(((double)j - 1 - a) * (N - j + 1) / (j - 1));
   return fact + orc_S(tb, N - l, M) - orc_S(tb, N, M + 1);
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* table-indicator Gibbs step of the reference's demo, test/demo.c:405-434                     */
+/* ------------------------------------------------------------------------------------------ */
+/*
+ * One or more sweeps over the tokens of R restaurants (restaurant j: tokens tok_dish[tok_off[j] .. tok_off[j+1]),
+ * counts n[j*D + i], table counts t[j*D + i], T[j] = sum_i t[j][i]).  Per token of dish i with n > 1: the
+ * indicator is removed with probability (t-1)/(n-1) (drawn only when t > 1, :418-422), then added with probability
+ * one/(one+1), one = H[i] (b + T a) t / (n - t + 1) V^n_{t+1} as a float (:425-430).  Uniforms come from glibc's
+ * 48-bit generator (erand48 = drand48 with an explicit state, lib/srng.h:28-34): shared != 0 is the demo's schedule
+ * (one stream, restaurants in order), otherwise restaurant j runs on its own stream rng[j].
+ */
+static void orc_ti_restaurant(const orc_table *tb, double apar, double bpar, const uint32_t *dish, uint32_t ntok,
+                              const float *H, const uint32_t *n, uint16_t *t, uint32_t *Tj, unsigned short xs[3]) {
+  uint32_t c;
+  for (c = 0; c < ntok; c++) {
+    const uint32_t i = dish[c];
+    float one;
+    if (n[i] == 1) continue;
+    if (t[i] > 1 && (n[i] - 1) * erand48(xs) < (t[i] - 1)) {
+      t[i]--;
+      (*Tj)--;
+    }
+    one = H[i] * (bpar + *Tj * apar) * (t[i]) / (n[i] - t[i] + 1) * orc_V(tb, n[i], t[i] + 1);
+    if (erand48(xs) < one / (one + 1.0)) {
+      t[i]++;
+      (*Tj)++;
+    }
+  }
+}
+
+static void orc_unpack48(uint64_t x, unsigned short xs[3]) {
+  xs[0] = (unsigned short)(x & 0xFFFF);
+  xs[1] = (unsigned short)((x >> 16) & 0xFFFF);
+  xs[2] = (unsigned short)((x >> 32) & 0xFFFF);
+}
+static uint64_t orc_pack48(const unsigned short xs[3]) { return (uint64_t)xs[0] | ((uint64_t)xs[1] << 16) | ((uint64_t)xs[2] << 32); }
+
+void orc_ti_gibbs(const orc_table *tb, double apar, double bpar, size_t R, const uint32_t *tok_off, const uint32_t *tok_dish,
+                  const float *H, uint32_t D, const uint32_t *n, uint16_t *t, uint32_t *T, uint64_t *rng, int shared,
+                  int sweeps) {
+  unsigned short xs[3];
+  size_t j;
+  int s;
+  if (shared) {
+    orc_unpack48(rng[0], xs);
+    for (s = 0; s < sweeps; s++)
+      for (j = 0; j < R; j++)
+        orc_ti_restaurant(tb, apar, bpar, tok_dish + tok_off[j], tok_off[j + 1] - tok_off[j], H, n + j * D, t + j * D, &T[j], xs);
+    rng[0] = orc_pack48(xs);
+    return;
+  }
+  for (j = 0; j < R; j++) {
+    orc_unpack48(rng[j], xs);
+    for (s = 0; s < sweeps; s++)
+      orc_ti_restaurant(tb, apar, bpar, tok_dish + tok_off[j], tok_off[j + 1] - tok_off[j], H, n + j * D, t + j * D, &T[j], xs);
+    rng[j] = orc_pack48(xs);
+  }
+}

@@ -48,6 +48,11 @@ void orc_partition_node(const orc_table *tb, double a, unsigned n, unsigned t, c
                         int exact);
 double orc_partition_logp(const orc_table *tb, double a, unsigned N, unsigned M, unsigned l);
 
+/* the table-indicator Gibbs step of test/demo.c:405-434 over R restaurants: see stirling_oracle.c */
+void orc_ti_gibbs(const orc_table *tb, double apar, double bpar, size_t R, const uint32_t *tok_off, const uint32_t *tok_dish,
+                  const float *H, uint32_t D, const uint32_t *n, uint16_t *t, uint32_t *T, uint64_t *rng, int shared,
+                  int sweeps);
+
 /* number of stored cells with m>=2, SURVEY.md section 8 */
 uint64_t orc_cells_S(uint64_t N, uint64_t M);
 uint64_t orc_cells_V(uint64_t N, uint64_t M);

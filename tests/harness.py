@@ -44,6 +44,10 @@ def oracle() -> C.CDLL:
         L.orc_asympt.restype, L.orc_asympt.argtypes = d, [d, u, u]
         L.orc_V_asympt.restype, L.orc_V_asympt.argtypes = d, [d, u, u]
         L.orc_logminus.restype, L.orc_logminus.argtypes = d, [d, d]
+        u32p = C.POINTER(C.c_uint32)
+        L.orc_ti_gibbs.restype = None
+        L.orc_ti_gibbs.argtypes = [vp, d, d, C.c_size_t, u32p, u32p, C.POINTER(C.c_float), C.c_uint32, u32p,
+                                   C.POINTER(C.c_uint16), u32p, C.POINTER(C.c_uint64), C.c_int, C.c_int]
         L.orc_partition_node.restype = None
         L.orc_partition_node.argtypes = [vp, d, u, u, dp, C.POINTER(C.c_uint16), C.c_int]
         L.orc_partition_logp.restype, L.orc_partition_logp.argtypes = d, [vp, d, u, u, u]

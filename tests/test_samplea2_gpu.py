@@ -133,3 +133,54 @@ def test_samplea2_exact_mode_and_ars_mode():
     finally:
         L.stb_set_partition_mode(stb.STB_PARTITION_REFERENCE)
         tab.free()
+
+
+@pytest.mark.parametrize("exact", [False, True])
+@pytest.mark.parametrize("seed,I,K,nmax,loops", [(42, 6, 8, 300, 1), (7, 10, 12, 1500, 2)])
+def test_samplea2_batch_equals_the_scalar_call_chain_by_chain(seed, I, K, nmax, loops, exact):
+    """samplea2 batched over chains (one table per chain from the sweep, the partition kernel over
+    chains x nodes with the uniforms made on the device from each chain's stream, the likelihood a device
+    reduction over the chain's histogram of sizes).  Chain c's discount and stream must equal the scalar
+    samplea2's on a table at a0[c] with the stream of the same seed -- and the scalar call equals the reference's
+    -DSAMPLEA_M build bit for bit (test above)."""
+    (n_rows, t_rows), libc = probe_counts(seed, I, K, nmax)
+    L = stb.lib()
+    cts = stb.Counts(n_rows, t_rows)
+    bpar = np.full(I, 10.0)
+    a0 = np.array([0.15, 0.3, 0.5, 0.5, 0.7, 0.9])
+    seeds = [900 + seed + 13 * c for c in range(a0.shape[0])]
+    maxn = max(int(r.max()) for r in n_rows) + 1
+    maxt = max(int(r.max()) for r in t_rows) + 1
+    old = L.stb_set_partition_mode(stb.STB_PARTITION_EXACT if exact else stb.STB_PARTITION_REFERENCE)
+    try:
+        want_a, want_next = [], []
+        for c, (ac, sd) in enumerate(zip(a0, seeds)):
+            tab = stb.Table(maxn, maxt, maxn, maxt, float(ac), stb.S_STABLE)
+            libc.srand48(sd)
+            want_a.append(_call_samplea2(L, tab, float(ac), n_rows, t_rows, loops))
+            want_next.append(libc.drand48())
+            tab.free()
+        rng = np.array([L.stb_rng48_state(sd) for sd in seeds], dtype=np.uint64)
+        a1, rng1, stats = stb.samplea2_batch(a0, cts, bpar, rng, loops=loops)
+        got_next = [L.stb_rng48_drand(C.byref(C.c_uint64(int(x)))) for x in rng1]
+        assert got_next == want_next, "a chain's stream is out of step with the scalar call's"
+        assert [float(x) for x in a1] == [float(x) for x in want_a]
+        assert stats["evals"] >= a0.shape[0] * loops
+    finally:
+        L.stb_set_partition_mode(old)
+
+
+def test_samplea2_batch_many_chains_in_bounds():
+    """more chains than one wave of tables holds; every draw inside the slice sampler's bounds"""
+    (n_rows, t_rows), _ = probe_counts(9, 12, 20, 800)
+    L = stb.lib()
+    cts = stb.Counts(n_rows, t_rows)
+    Cn = 700
+    a0 = 0.05 + 0.9 * (np.arange(Cn) + 0.5) / Cn
+    rng = np.array([L.stb_rng48_state(5000 + c) for c in range(Cn)], dtype=np.uint64)
+    a1, rng1, stats = stb.samplea2_batch(a0, cts, np.full(12, 10.0), rng, loops=1)
+    assert ((a1 >= np.maximum(0.01, a0 - stb_squeeze()) - 1e-12) & (a1 <= 0.98)).all()
+    assert (rng1 != rng).all() and (a1 != a0).any()
+    # the same chains in two halves: a chain's result does not depend on who runs beside it
+    a2, rng2, _ = stb.samplea2_batch(a0[:300], cts, np.full(12, 10.0), rng[:300], loops=1)
+    assert np.array_equal(a2, a1[:300]) and np.array_equal(rng2, rng1[:300])
