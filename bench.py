@@ -282,10 +282,10 @@ def run_extras():
     _, sums, last = w.run(a, gather=False, sums=True, lastrow=True)
     wall = time.perf_counter() - t0
     cells = cells_S(N3, M3) * NA3
-    T = w.tables_in_flight
+    T, TL = w.tables_in_flight, w.tables_per_launch
     waves = -(-NA3 // T)
-    out["config3_sweep"] = {"discounts": NA3, "of": NA3, "tables_per_launch": T, "waves": waves,
-                            "wave_quantisation": NA3 / (waves * T),
+    out["config3_sweep"] = {"discounts": NA3, "of": NA3, "tables_side_by_side": T, "tables_per_launch": TL,
+                            "launches": -(-NA3 // TL), "wave_quantisation": NA3 / (waves * T),
                             "cells_per_s_device": cells / (w.last_fill_ms * 1e-3), "cells_per_s_e2e": cells / wall,
                             "device_ms": w.last_fill_ms, "wall_s": wall,
                             "hbm_frac": cells * 8 / (w.last_fill_ms * 1e-3) / 1e9 / 6544.7,
@@ -354,6 +354,10 @@ def run_extras():
     except Exception as exc:
         out["config4_samplea2"] = {"error": repr(exc)}
     try:
+        _extras_gibbs(out, stb)
+    except Exception as exc:
+        out["gibbs_table_indicators"] = {"error": repr(exc)}
+    try:
         _extras_dropin_default(out)
     except Exception as exc:
         out["config1_dropin_default_flags"] = {"error": repr(exc)}
@@ -384,6 +388,59 @@ def _extras_dropin_default(out):
     res["what"] = ("S_make(10000,1000,10000,1000,0.5,S_STABLE|S_UVTABLE); 20 x (S_remake + one S_V); 1e7 scalar S_V at random (n,m); "
                    "default flags: the host mirror serves the scalar calls (pinned 4 MB row blocks fetched on first touch, kept across refills)")
     out["config1_dropin_default_flags"] = res
+
+
+def _extras_gibbs(out, stb):
+    """table-indicator Gibbs sweeps (test/demo.c:405-434) with V read from the device table --
+    20 000 restaurants x 50 dishes, ~2 000 tokens each, one 48-bit stream per restaurant; the oracle's restatement of
+    the reference loop (CPU table, erand48) runs a sample of the restaurants beside it and must give the same counts"""
+    import numpy as np
+
+    from tests import harness
+
+    rs = np.random.default_rng(11)
+    R, D, mean = 20000, 50, 2000
+    pop = 1.0 / np.arange(1, D + 1) ** 0.8
+    pop /= pop.sum()
+    ntok = np.maximum(1, rs.poisson(mean, size=R))
+    off = np.zeros(R + 1, dtype=np.uint32)
+    off[1:] = np.cumsum(ntok)
+    tok = rs.choice(D, size=int(off[-1]), p=pop).astype(np.uint32)
+    n = np.zeros((R, D), dtype=np.uint32)
+    np.add.at(n, (np.repeat(np.arange(R), ntok), tok), 1)
+    t = (n > 0).astype(np.uint16)
+    T = t.sum(axis=1).astype(np.uint32)
+    H = (pop * D).astype(np.float32)
+    N = int(n.max())
+    a, b, sweeps = 0.5, 10.0, 4
+    tab = stb.Table(N, N, N, N, a, stb.S_STABLE | stb.S_UVTABLE)
+    L = stb.lib()
+    rng = np.array([L.stb_rng48_state(100 + j) for j in range(R)], dtype=np.uint64)
+    tab.ti_gibbs(b, off[:101], tok[: off[100]], H, n[:100], t[:100], T[:100], rng[:100], sweeps=1)  # warm-up
+    t0 = time.perf_counter()
+    t1, T1, r1 = tab.ti_gibbs(b, off, tok, H, n, t, T, rng, sweeps=sweeps)
+    wall = time.perf_counter() - t0
+    res = {"restaurants": R, "dishes": D, "tokens": int(off[-1]), "sweeps": sweeps, "table": [N, N],
+           "kernel_ms": tab.last_gibbs_ms, "wall_ms": wall * 1e3,
+           "token_updates_per_s_device": int(off[-1]) * sweeps / (tab.last_gibbs_ms * 1e-3),
+           "token_updates_per_s_e2e": int(off[-1]) * sweeps / wall}
+    tab.free()
+    # CPU: the oracle's restatement of the reference loop on the first 200 restaurants, one core
+    O = harness.oracle()
+    tb = O.orc_make(N, N, N, N, a, 3)
+    Rs = 200
+    t2, T2, r2 = t[:Rs].copy(), T[:Rs].copy(), rng[:Rs].copy()
+    u32p = C.POINTER(C.c_uint32)
+    offs, toks, ns = off[: Rs + 1].copy(), tok[: off[Rs]].copy(), np.ascontiguousarray(n[:Rs])
+    t0 = time.perf_counter()
+    O.orc_ti_gibbs(tb, a, b, Rs, offs.ctypes.data_as(u32p), toks.ctypes.data_as(u32p), H.ctypes.data_as(C.POINTER(C.c_float)), D,
+                   ns.ctypes.data_as(u32p), t2.ctypes.data_as(C.POINTER(C.c_uint16)), T2.ctypes.data_as(u32p),
+                   r2.ctypes.data_as(C.POINTER(C.c_uint64)), 0, sweeps)
+    cpu = time.perf_counter() - t0
+    O.orc_free(tb)
+    res["cpu_port"] = {"restaurants": Rs, "token_updates_per_s": int(off[Rs]) * sweeps / cpu, "cores": 1,
+                       "counts_equal": bool(np.array_equal(t2, t1[:Rs]) and np.array_equal(r2, r1[:Rs]))}
+    out["gibbs_table_indicators"] = res
 
 
 def _extras_samplea2(out, stb, cts, bpar):
@@ -425,6 +482,26 @@ def _extras_samplea2(out, stb, cts, bpar):
     a1 = L.samplea2(a0, tab.sp, *cts.args(), None, bpar.ctypes.data_as(C.POINTER(d)), None, 1, 0)
     res["samplea2_call"] = {"wall_ms": (time.perf_counter() - t0) * 1e3, "a": a1}
     tab.free()
+    # the same update for many chains at once (stb_samplea2_batch): one table per chain from the sweep, the
+    # partition kernel over chains x nodes, the likelihood a device reduction over size histograms
+    try:
+        Cb = 256
+        ab = 0.05 + 0.9 * (np.arange(Cb) + 0.5) / Cb
+        rb = np.array([L.stb_rng48_state(12345 + c) for c in range(Cb)], dtype=np.uint64)
+        stb.samplea2_batch(ab[:16], cts, bpar, rb[:16])  # warm-up
+        t0 = time.perf_counter()
+        a2b, _, sb = stb.samplea2_batch(ab, cts, bpar, rb)
+        wall = time.perf_counter() - t0
+        libc.srand48(12345 + 128)
+        tab1 = stb.Table(maxn, maxt, maxn, maxt, float(ab[128]), stb.S_STABLE)
+        a_scalar = L.samplea2(float(ab[128]), tab1.sp, *cts.args(), None, bpar.ctypes.data_as(C.POINTER(d)), None, 1, 0)
+        tab1.free()
+        res["samplea2_batch"] = {"chains": Cb, "wall_ms": wall * 1e3, "ms_per_chain": wall * 1e3 / Cb, "device_ms": sb["eval_ms"],
+                                 "evals": int(sb["evals"]), "rounds": int(sb["rounds"]),
+                                 "in_bounds": bool(((a2b >= 0.01) & (a2b <= 0.98)).all()),
+                                 "chain128_equals_scalar_call": bool(a2b[128] == a_scalar)}
+    except Exception as exc:
+        res["samplea2_batch"] = {"error": repr(exc)}
     ref_so = os.path.join(ROOT, "oracle", "_ref", "libstb_ref_slice_m.so")
     if os.path.exists(ref_so):  # the reference built with -DSAMPLEA_M, one host core, the same call
         R = C.CDLL(ref_so)
@@ -754,8 +831,9 @@ def run_own_sweep(args):
         # a kernel timed inside a long step: the sustained figure when the driver wrote one
         peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks \
             else (6650.0, "fallback (B200_PROFILING.md)")
-        T = w.tables_in_flight
+        T, TL = w.tables_in_flight, w.tables_per_launch
         waves = -(-mine.shape[0] // T)
+        launches = -(-mine.shape[0] // TL)
         ms_step = 1e3 * dev_s / args.steps
         achieved = cells_tab * mine.shape[0] * 8 / (sum(fill_ms) / len(fill_ms) * 1e-3) / 1e9  # this rank's kernel
         line = {
@@ -767,20 +845,21 @@ def run_own_sweep(args):
                             f"({cells_tab * na:.3e} cells, {cells_tab * na * 8 / 1e12:.2f} TB written per step), table j on rank j mod {world}; "
                             f"kept per table: the sum over {NPAIRS3} (n,m) look-ups and the last row, all_gather (NCCL) of both at the "
                             f"end of the step; no traffic between GPUs during the fills",
-                "l2": "every wave of tables (6 x 1.9 GB per GPU) overwrites the slabs of the previous one (>> 126 MB L2)",
+                "l2": f"every launch fills {TL} tables ({T} side by side x {TL // max(T, 1)} rounds, 1.9 GB each) into resident slabs "
+                      "that the next launch overwrites (>> 126 MB L2)",
                 "timing": "value: CUDA events around each rank's queue of fills and reductions, summed over steps, max over "
                           "ranks; e2e: wall clock of the whole step (C-ABI call with host result buffers + gather), max over ranks",
-                "wave_quantisation": {"tables_per_launch": T, "waves_per_rank": waves,
-                                      "efficiency": mine.shape[0] / (waves * T)},
+                "wave_quantisation": {"tables_side_by_side": T, "tables_per_launch": TL, "launches_per_rank": launches,
+                                      "rounds_per_rank": waves, "efficiency": mine.shape[0] / (waves * T)},
                 "device_s_each_rank": dev_each,
                 "parity_spot_check": bool(ok),
             },
             "e2e": {"value": cells_tab * na * args.steps / wall, "unit": "cells/s", "h2d_bytes_per_step": 8 * mine.shape[0] * world,
                     "d2h_bytes_per_step": 8 * (1 + M3) * na, "ms_per_step": 1e3 * wall / args.steps},
-            "gpu_launches": args.steps * waves * 3 * world,
+            "gpu_launches": args.steps * launches * 3 * world,  # per launch: the fill, the gather of the look-ups, the sums
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel": "stb::fill_strip_kernel (per GPU, rank 0's launches)",
-                         "kernel_ms": sum(fill_ms) / len(fill_ms) / waves},
+                         "kernel_ms": sum(fill_ms) / len(fill_ms) / launches},
             "clocks": clocks,
             "extras": {"c_abi_multi_device": cabi, "config4_chains_sharded": chains},
         }

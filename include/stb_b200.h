@@ -90,9 +90,11 @@ int stb_sweep_set_pairs(stb_sweep_t *w, const uint32_t *n, const uint32_t *m, si
 int stb_sweep_run(stb_sweep_t *w, const double *a, size_t na, double *gather_out, double *sum_out,
                   double *lastrow_out);
 /* device milliseconds of the most recent stb_sweep_run (CUDA events around its queue of fills and
- * reductions: the fills are > 99 % of it); tables filled per launch */
+ * reductions: the fills are > 99 % of it); tables a launch fills side by side (one CTA group each), and tables
+ * per launch in all -- a launch fills several rounds of them back to back into as many resident slabs */
 double stb_sweep_last_fill_ms(const stb_sweep_t *w);
 int stb_sweep_tables_in_flight(const stb_sweep_t *w);
+int stb_sweep_tables_per_launch(const stb_sweep_t *w);
 void stb_sweep_free(stb_sweep_t *w);
 
 /*

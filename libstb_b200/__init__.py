@@ -59,6 +59,7 @@ def lib() -> C.CDLL:
     L.stb_sweep_run.restype, L.stb_sweep_run.argtypes = C.c_int, [vp, dp, C.c_size_t, dp, dp, dp]
     L.stb_sweep_last_fill_ms.restype, L.stb_sweep_last_fill_ms.argtypes = d, [vp]
     L.stb_sweep_tables_in_flight.restype, L.stb_sweep_tables_in_flight.argtypes = C.c_int, [vp]
+    L.stb_sweep_tables_per_launch.restype, L.stb_sweep_tables_per_launch.argtypes = C.c_int, [vp]
     L.stb_sweep_free.restype, L.stb_sweep_free.argtypes = None, [vp]
     L.stb_sweep_multi_create.restype = vp
     L.stb_sweep_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, u, u, C.c_uint32]
@@ -320,6 +321,9 @@ class Sweep:
     def last_fill_ms(self): return self._L.stb_sweep_last_fill_ms(self.w)
     @property
     def tables_in_flight(self): return self._L.stb_sweep_tables_in_flight(self.w)
+
+    @property
+    def tables_per_launch(self): return self._L.stb_sweep_tables_per_launch(self.w)
 
     def free(self):
         if self.w:

@@ -333,14 +333,31 @@ __device__ __forceinline__ void sts_s32_if(unsigned a, int v, bool pred) {
  * rescale), a product of two powers of two, converts them exactly.  Everything is stored unconditionally: rows that do not exist (before the
  * strip's first row, past N) land in ring slots the consumers never read as valid.
  */
+#ifndef STB_NB_EARLY
+#define STB_NB_EARLY 0  // 1: the neighbour load of step i+1 issued in step i, right behind the store that makes it readable (two steps of latency instead of one): measured 1.2 % SLOWER on config 2 (9.35 against 9.24 ms) -- the load is not what holds the producer up
+#endif
+__device__ __forceinline__ void lds_f64_if(double &v, unsigned a, bool pred) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.u32 p, %2, 0;\n\t"
+      "@p ld.volatile.shared.f64 %0, [%1];\n\t}"
+      : "+d"(v)
+      : "r"(a), "r"((unsigned)pred));
+}
 template <int K, bool HAS_V, bool DUP, int CP, int RS, bool FIRST, bool OUT>
-__device__ __forceinline__ void strip_steps(double (&x)[K], const double (&ma)[K], double &nm1, double &yin,
-                                            const unsigned first_addr, const double scn0, const double scn,
+__device__ __forceinline__ void strip_steps(double (&x)[K], const double (&ma)[K], double &nm1, double &yin, double &nbp,
+                                            const bool lane0, const unsigned first_addr, const double scn0, const double scn,
                                             unsigned &nb_addr,
                                             const unsigned nb_stride, const bool write_out, const unsigned xr,
                                             const unsigned yr, const unsigned outp) {
 #pragma unroll
   for (int i = 0; i < ST_RB; i++) {
+#if STB_NB_EARLY
+    // (the load of this step's neighbour value was issued in the PREVIOUS step, right behind the store that made it
+    // readable -- see below; only lane 0, which reads the boundary ring, fetches the first entry of a batch here,
+    // once the batch's flow control has made sure that it is there)
+    if (FIRST && i == 0) lds_f64_if(nbp, first_addr, lane0);
+#else
     double nb;
     if (FIRST && i == 0)
       nb = lds_f64(first_addr);
@@ -348,6 +365,7 @@ __device__ __forceinline__ void strip_steps(double (&x)[K], const double (&ma)[K
       nb = lds_f64(nb_addr);
       nb_addr += nb_stride;
     }
+#endif
     // Stores (kept in program order) are placed where their operands are long since ready: columns
     // 0..K-2 of the PREVIOUS row go out now, before this step's arithmetic; only column K-1 -- the
     // one the right-hand neighbour reads back in its next step -- is stored in its own step, and
@@ -372,7 +390,18 @@ __device__ __forceinline__ void strip_steps(double (&x)[K], const double (&ma)[K
     sts_f64(xr + (i * CP + K - 1) * 8, x[K - 1]);
     if (DUP) sts_f64(xr + ((RS + i) * CP + K - 1) * 8, x[K - 1]);
     if (OUT) sts_f64_if(outp + i * 8, x[K - 1], write_out);  // (G == 1: the flusher takes the column from the x ring)
+#if STB_NB_EARLY
+    // The left neighbour has just stored the value this lane needs in step i+2 (one instruction of the warp ago):
+    // the load goes out NOW and is first used at the bottom of the NEXT step -- almost two steps of latency it may
+    // take, where a load at the top of the next step had one (under the consumers' shared-memory traffic the
+    // producer stalled ~10 cycles a row on it).  What this step hands on (yin, for step i+1) was loaded a step ago.
+    const double nbn = lds_f64(nb_addr);
+    nb_addr += nb_stride;
+    yin = nbp * ((FIRST && i == 0) ? scn0 : scn);
+    nbp = nbn;
+#else
     yin = nb * ((FIRST && i == 0) ? scn0 : scn);
+#endif
   }
   // the last row's remaining columns
   if (HAS_V) {
@@ -432,6 +461,7 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
   // S^rs_rs = 1 (S^0_0 = 1 for the first strip) seeds the strip's diagonal; with phi > 0 it
   // arrives through the boundary ring like every other row
   double yin = (lane == 0 && (g.phi == 0 || !has_left)) ? 1.0 : 0.0;
+  double nbp = 0.0;  // the neighbour value in flight (STB_NB_EARLY): batch 0 reads "the previous batch's last row", zeros
   const bool lane0 = (lane == 0);
   const bool take_bnd = lane0 && has_left;  // lane 0 of the first strip reads zeros times zero
   const bool write_out = has_right && (lane == L - 1);
@@ -477,6 +507,7 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
   long long dbgacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   unsigned long long gt_start = 0;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_start));
+  const long long ck_start = clock64();
 #endif
   // words fetched ahead of need (mid-batch), so that the checks at the top of a batch rarely load
   int2 gen_next = make_int2(0, 0);
@@ -498,7 +529,7 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
         const long long tw0 = clock64();
         const int2 gq = lds_v2s32(a_gen + s0 * 4);
         const int wq = has_left ? lds_s32(a_in_written) : 0, tq = has_right ? lds_s32(a_out_taken) : 0;
-        const int why = (gq.x < gen_need || gq.y < gen_need) ? 1 : (wq < need_in ? 2 : (tq < need_out ? 6 : 7));
+        const int why = (gq.x < gen_need || gq.y < gen_need) ? 1 : (wq < need_in ? 7 : (tq < need_out ? 6 : 7));
         if (!producer_wait(a_gen + s0 * 4, gen_need, a_in_written, need_in, a_out_taken, need_out, P.abort_flag)) return;
         dbgacc[why] += clock64() - tw0;
       }
@@ -534,11 +565,11 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
     ST_TICK(tk3);
     // ---- sixteen steps, eight per consumer slot; only ring rows 0..7 have duplicates ----
     if (s0 == 0)
-      strip_steps<K, HAS_V, true, CP, RS, true, OUT>(x, ma, nm1, yin, first_addr, scn0, scn, nb_addr, nb_stride, write_out, xr,
-                                                yr, outp);
+      strip_steps<K, HAS_V, true, CP, RS, true, OUT>(x, ma, nm1, yin, nbp, lane0, first_addr, scn0, scn, nb_addr, nb_stride,
+                                                     write_out, xr, yr, outp);
     else
-      strip_steps<K, HAS_V, false, CP, RS, true, OUT>(x, ma, nm1, yin, first_addr, scn0, scn, nb_addr, nb_stride, write_out,
-                                                 xr, yr, outp);
+      strip_steps<K, HAS_V, false, CP, RS, true, OUT>(x, ma, nm1, yin, nbp, lane0, first_addr, scn0, scn, nb_addr, nb_stride,
+                                                      write_out, xr, yr, outp);
     // mid-batch: fetch the words the NEXT batch's flow control will look at, fix the next scale
     {
       int s1 = s0 + 2;
@@ -555,7 +586,7 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
       asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a_er + (((p + 1) & (ST_NJ - 1)) * 32) * 4),
                    "r"((unsigned)elow_n + (0x80000000u - 1023u)));
     }
-    strip_steps<K, HAS_V, false, CP, RS, false, OUT>(x, ma, nm1, yin, 0u, scn, scn, nb_addr, nb_stride, write_out,
+    strip_steps<K, HAS_V, false, CP, RS, false, OUT>(x, ma, nm1, yin, nbp, lane0, 0u, scn, scn, nb_addr, nb_stride, write_out,
                                                 xr + ST_RB * CP * 8, yr + (HAS_V ? ST_RB * 32 * 8 : 0),
                                                 outp + ST_RB * 8);
     ST_TICK(tk4);
@@ -586,6 +617,7 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
     unsigned long long gt_end;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_end));
     d[7] = (long long)(gt_end - gt_start);
+    d[2] = clock64() - ck_start;  // (slot 2, "left boundary", moves to the print below: cycles of the whole producer)
     d[5] = dbgacc[5];
   }
 #endif
@@ -1433,7 +1465,8 @@ inline int strip_fill(StripState *st, const StripFillArgs &A, cudaStream_t strea
                     "cta %3d producer %d batches %6.0f cycles/batch: flow-control %.0f - %.0f - %.0f setup %.0f "
                     "steps %.0f publish %.0f | busy %.1f us\n",
                     c, gi, nb, d[0] / nb, d[1] / nb, d[2] / nb, (d[3] & ((1ll << 40) - 1)) / nb, d[4] / nb, d[5] / nb, d[7] / 1e3);
-            fprintf(stderr, "          (flow control: ring slots %.0f, left boundary %.0f, flusher %.0f)\n", d[1] / nb, d[2] / nb, (d[3] >> 40) / nb);
+            fprintf(stderr, "          (flow control: ring slots %.0f, flusher %.0f; %.0f cycles per batch in all, SM clock %.0f MHz)\n",
+                    d[1] / nb, (d[3] >> 40) / nb, d[2] / nb, d[2] / (d[7] / 1e3));
           }
         }
       }

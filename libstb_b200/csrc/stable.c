@@ -678,6 +678,7 @@ int stb_sweep_hist_eval(stb_sweep_t *w, const double *x, const int *chain, size_
 }
 double stb_sweep_last_fill_ms(const stb_sweep_t *w) { return w->last_ms; }
 int stb_sweep_tables_in_flight(const stb_sweep_t *w) { return stb_cuda_sweep_tables_in_flight(w->dev); }
+int stb_sweep_tables_per_launch(const stb_sweep_t *w) { return stb_cuda_sweep_tables_per_launch(w->dev); }
 void stb_sweep_free(stb_sweep_t *w) {
   if (!w) return;
   stb_cuda_sweep_destroy(w->dev);

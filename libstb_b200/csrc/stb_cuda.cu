@@ -844,6 +844,7 @@ extern "C" stb_sweep_dev_t *stb_cuda_sweep_create(unsigned N, unsigned M, int is
 }
 
 extern "C" int stb_cuda_sweep_tables_in_flight(const stb_sweep_dev_t *w) { return w->T; }
+extern "C" int stb_cuda_sweep_tables_per_launch(const stb_sweep_dev_t *w) { return w->slabs; }
 
 extern "C" int stb_cuda_sweep_set_pairs(stb_sweep_dev_t *w, const uint32_t *n, const uint32_t *m, size_t npairs) {
   ON_DEVICE(w->device);

@@ -127,6 +127,7 @@ int stb_cuda_sweep_run_dealt(stb_sweep_dev_t *w, const double *a, size_t na, siz
                              double *gather_out, double *sum_out, double *lastrow_out, float *fill_ms);
 /* tables one launch fills side by side for this extent on this device */
 int stb_cuda_sweep_tables_in_flight(const stb_sweep_dev_t *w);
+int stb_cuda_sweep_tables_per_launch(const stb_sweep_dev_t *w);
 /* samplea2 over many chains (stb_cuda.cu): nodes of the partition step, the step itself against one table per
  * chain, and the evaluation of the likelihood's table terms from the per-chain histograms of sampled sizes */
 int stb_cuda_sweep_set_nodes(stb_sweep_dev_t *w, const uint32_t *n, const uint16_t *t, const uint32_t *draw, size_t count,

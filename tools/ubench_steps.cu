@@ -67,7 +67,7 @@ __global__ void steps_kernel(long long *cycles, double *sink, int batches, doubl
   for (int i = lane; i < (RS + 8) * CP + (RS + 8) * 32 + 64; i += 32) xring[i] = 0.0;
   double x[K], ma[K];
   for (int k = 0; k < K; k++) { x[k] = 0.0; ma[k] = (double)(1 + lane * K + k) * a; }
-  double nm1 = (double)(-lane), yin = lane == 0 ? 1.0 : 0.0;
+  double nm1 = (double)(-lane), yin = lane == 0 ? 1.0 : 0.0, nbp = 0.0;
   long long E = 0;
   const unsigned a_xr = smem_u32(xring + lane * K), a_yr = smem_u32(yring + lane), a_out = smem_u32(outx);
   const unsigned nb_stride = lane == 0 ? 8u : (unsigned)(CP * 8);
@@ -87,8 +87,8 @@ __global__ void steps_kernel(long long *cycles, double *sink, int batches, doubl
     const double scn = lane == 0 ? 0.0 : pow2i(sE - elow);
     unsigned nb_addr = lane == 0 ? a_out + 8u : a_xr - 8u;
     if (MODE == 0) {  // MODE 128: steps_var with everything on
-      strip_steps<K, false, false, CP, RS, true, true>(x, ma, nm1, yin, lane == 0 ? a_out : a_xr + 15 * CP * 8 - 8u, scn, scn, nb_addr, nb_stride, lane == 31, a_xr, a_yr, a_out);
-      strip_steps<K, false, false, CP, RS, false, true>(x, ma, nm1, yin, 0u, scn, scn, nb_addr, nb_stride, lane == 31, a_xr + 8 * CP * 8,
+      strip_steps<K, false, false, CP, RS, true, true>(x, ma, nm1, yin, nbp, lane == 0, lane == 0 ? a_out : a_xr + 15 * CP * 8 - 8u, scn, scn, nb_addr, nb_stride, lane == 31, a_xr, a_yr, a_out);
+      strip_steps<K, false, false, CP, RS, false, true>(x, ma, nm1, yin, nbp, lane == 0, 0u, scn, scn, nb_addr, nb_stride, lane == 31, a_xr + 8 * CP * 8,
                                                   a_yr, a_out + 64);
     } else {
       steps_var<K, CP, MODE>(x, ma, nm1, yin, scn, nb_addr, nb_stride, a_xr);
