@@ -783,8 +783,16 @@ __device__ void strip_consumer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
     }
 #endif
     ST_CTICK(1);  // wait for the rows
-    if (r0 >= cvalid && r0 <= r_fast_hi) {
-      // (rows strictly below the strip's diagonal: the diagonal itself is the edge path's)
+    // The strip's first cvalid rows are its triangle (column col exists from row r = col on).  Its units take the
+    // same unrolled path as the rest, with one more store predicate per row (col <= r); a unit that lies above the
+    // diagonal altogether has nothing to do.  (They used to go through the per-cell edge function: ~100 slow units
+    // at the start of EVERY strip, and since no CTA can run faster than its left neighbour, what a strip loses at
+    // its start it never makes up -- the lost time ADDS UP along the chain of CTAs: 125 independent 160-column
+    // tables side by side fill in 8.20 ms, the 125-CTA chain of config 2 took 9.24.)
+    const bool tri = r0 < cvalid;
+    if (tri && r0 + ST_RB <= 32 * kk) {
+      // (every cell of the unit is above the diagonal)
+    } else if (r0 <= r_fast_hi) {
       // (tried: a variant for strips whose consumers are a multiple of the column blocks -- every warp keeps its
       // block, the column's geometry hoisted out of the loop: 4 % SLOWER on config 2, 9.44 against 9.04 ms)
       const int col = lane + 32 * kk;
@@ -812,10 +820,19 @@ __device__ void strip_consumer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
 #pragma unroll
         for (int i = 0; i < ST_RB; i++) v[i] = log_scaled_r<LOGTAB_REP8>(xv[i], (i + sh >= (unsigned)ST_B) ? Eb : Ea, logtab);
         unsigned long long ga = row_addr(gS0, pitchb, (unsigned)r0) + (unsigned)col * ES;
+        if (!tri) {
 #pragma unroll
-        for (int i = 0; i < ST_RB; i++) {
-          stg_if(ga, v[i], lane_ok, (OutT *)nullptr);
-          if (i + 1 < ST_RB) ga = row_addr(ga, pitchb, one);
+          for (int i = 0; i < ST_RB; i++) {
+            stg_if(ga, v[i], lane_ok, (OutT *)nullptr);
+            if (i + 1 < ST_RB) ga = row_addr(ga, pitchb, one);
+          }
+        } else {
+          const int lim = col - r0;  // row i of the unit holds column col when i >= lim
+#pragma unroll
+          for (int i = 0; i < ST_RB; i++) {
+            stg_if(ga, v[i], lane_ok && i >= lim, (OutT *)nullptr);
+            if (i + 1 < ST_RB) ga = row_addr(ga, pitchb, one);
+          }
         }
         if (FIRST && kk == 0) {  // S1: log S^n_1 in FP64 whatever the table stores
           if (lane == 0) {
@@ -835,10 +852,19 @@ __device__ void strip_consumer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
         for (int i = 0; i < ST_RB; i++) den[i] = (kq == 0) ? ycm[i * 32] : xcm[i * CP];
         const bool v_ok = FIRST ? (lane_ok && col != 0) : lane_ok;
         unsigned long long ga = row_addr(gV0, pitchb, (unsigned)r0) + (unsigned)col * ES;
+        if (!tri) {
 #pragma unroll
-        for (int i = 0; i < ST_RB; i++) {
-          stg_if(ga, div_pos(xv[i], den[i]), v_ok, (OutT *)nullptr);
-          if (i + 1 < ST_RB) ga = row_addr(ga, pitchb, one);
+          for (int i = 0; i < ST_RB; i++) {
+            stg_if(ga, div_pos(xv[i], den[i]), v_ok, (OutT *)nullptr);
+            if (i + 1 < ST_RB) ga = row_addr(ga, pitchb, one);
+          }
+        } else {
+          const int lim = col - r0;
+#pragma unroll
+          for (int i = 0; i < ST_RB; i++) {
+            stg_if(ga, div_pos(xv[i], den[i]), v_ok && i >= lim, (OutT *)nullptr);
+            if (i + 1 < ST_RB) ga = row_addr(ga, pitchb, one);
+          }
         }
       }
     } else {
