@@ -531,7 +531,7 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
         const int wq = has_left ? lds_s32(a_in_written) : 0, tq = has_right ? lds_s32(a_out_taken) : 0;
         const int why = (gq.x < gen_need || gq.y < gen_need) ? 1 : (wq < need_in ? 7 : (tq < need_out ? 6 : 7));
         if (!producer_wait(a_gen + s0 * 4, gen_need, a_in_written, need_in, a_out_taken, need_out, P.abort_flag)) return;
-        dbgacc[why] += clock64() - tw0;
+        if (why != 1) dbgacc[why] += clock64() - tw0;
       }
 #else
       if (!producer_wait(a_gen + s0 * 4, gen_need, a_in_written, need_in, a_out_taken, need_out, P.abort_flag)) return;
@@ -540,6 +540,13 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
       c_out = max(c_out, need_out);
     }
     ST_TICK(tk2);
+#ifdef STB_PROFILE_PRODUCER
+    if (p == 0) {  // when the strip's first batch starts (its input has arrived), ns since the kernel's start
+      unsigned long long gt_now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_now));
+      dbgacc[1] = (long long)(gt_now - gt_start);
+    }
+#endif
     // ---- the batch's scale (fixed half a batch ago) ----
     const int bs = jb & (ST_NBR - 1), os = p & (ST_NBR - 1);
 #pragma unroll
@@ -1479,8 +1486,8 @@ inline int strip_fill(StripState *st, const StripFillArgs &A, cudaStream_t strea
                       (double)d[0] / d[3], (double)d[1] / d[3], (double)d[2] / d[3]);
           }
         }
-        const int show[6] = {0, 1, 2, nctas / 2, nctas - 2, nctas - 1};
-        for (int si = 0; si < 6; si++) {
+        const int show[10] = {0, 1, 2, 3, nctas / 4, nctas / 2, nctas / 2 + 1, 3 * nctas / 4, nctas - 2, nctas - 1};
+        for (int si = 0; si < 10; si++) {
           const int c = show[si];
           if (c < 0 || c >= nctas || (si && c <= show[si - 1])) continue;
           for (int gi = 0; gi < pl.G; gi++) {
@@ -1491,8 +1498,8 @@ inline int strip_fill(StripState *st, const StripFillArgs &A, cudaStream_t strea
                     "cta %3d producer %d batches %6.0f cycles/batch: flow-control %.0f - %.0f - %.0f setup %.0f "
                     "steps %.0f publish %.0f | busy %.1f us\n",
                     c, gi, nb, d[0] / nb, d[1] / nb, d[2] / nb, (d[3] & ((1ll << 40) - 1)) / nb, d[4] / nb, d[5] / nb, d[7] / 1e3);
-            fprintf(stderr, "          (flow control: ring slots %.0f, flusher %.0f; %.0f cycles per batch in all, SM clock %.0f MHz)\n",
-                    d[1] / nb, (d[3] >> 40) / nb, d[2] / nb, d[2] / (d[7] / 1e3));
+            fprintf(stderr, "          (first batch started at %.1f us; flusher %.0f; %.0f cycles per batch in all, SM clock %.0f MHz)\n",
+                    d[1] / 1e3, (d[3] >> 40) / nb, d[2] / nb, d[2] / (d[7] / 1e3));
           }
         }
       }
