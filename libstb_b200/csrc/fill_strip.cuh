@@ -1333,11 +1333,19 @@ inline bool strip_plan(unsigned M, int slots, size_t elem_size, StripPlan *pl, b
   return false;
 }
 
-/* tables one launch fills side by side: each gets the CTAs its widest shape needs */
+/*
+ * Tables one launch fills side by side.  A table of more than one CTA is cut into 160-column strips (K = 5: the
+ * 16-slot ring) unless 224-column strips (K = 7: 12 slots, ~136 cycles per row against ~80) fit so many more
+ * tables into the launch that they win anyway; measured on config 3 (M = 5000): 4 tables x 32 CTAs 4.54e11 cells/s,
+ * 6 x 23 CTAs 4.26e11.  A table that fits ONE 224-column CTA stays there (the samplers' 5001 x 167: 2.9e11 against
+ * 2.2e11 as two 84-column CTAs).
+ */
 inline int strip_tables_per_launch(unsigned M, int num_sms) {
-  int pmin = (int)((M + 32u * 7u - 1) / (32u * 7u));
-  int per_launch = num_sms / (pmin > 0 ? pmin : 1);
-  return per_launch < 1 ? 1 : per_launch;
+  const int p7 = (int)((M + 32u * 7u - 1) / (32u * 7u)), p5 = (int)((M + 32u * 5u - 1) / (32u * 5u));
+  const int t7 = num_sms / (p7 > 0 ? p7 : 1) > 0 ? num_sms / (p7 > 0 ? p7 : 1) : 1;
+  const int t5 = num_sms / (p5 > 0 ? p5 : 1) > 0 ? num_sms / (p5 > 0 ? p5 : 1) : 1;
+  if (p7 <= 1) return t7;
+  return (t5 * 136 >= t7 * 80) ? t5 : t7;
 }
 
 struct StripFillArgs {
