@@ -416,10 +416,12 @@ def _extras_gibbs(out, stb):
     tab = stb.Table(N, N, N, N, a, stb.S_STABLE | stb.S_UVTABLE)
     L = stb.lib()
     rng = np.array([L.stb_rng48_state(100 + j) for j in range(R)], dtype=np.uint64)
-    tab.ti_gibbs(b, off[:101], tok[: off[100]], H, n[:100], t[:100], T[:100], rng[:100], sweeps=1)  # warm-up
-    t0 = time.perf_counter()
-    t1, T1, r1 = tab.ti_gibbs(b, off, tok, H, n, t, T, rng, sweeps=sweeps)
-    wall = time.perf_counter() - t0
+    tab.ti_gibbs(b, off, tok, H, n, t, T, rng, sweeps=1)  # warm-up at the timed size (first-touch of the staging buffers)
+    wall = float("inf")
+    for _ in range(2):
+        t0 = time.perf_counter()
+        t1, T1, r1 = tab.ti_gibbs(b, off, tok, H, n, t, T, rng, sweeps=sweeps)
+        wall = min(wall, time.perf_counter() - t0)
     res = {"restaurants": R, "dishes": D, "tokens": int(off[-1]), "sweeps": sweeps, "table": [N, N],
            "kernel_ms": tab.last_gibbs_ms, "wall_ms": wall * 1e3,
            "token_updates_per_s_device": int(off[-1]) * sweeps / (tab.last_gibbs_ms * 1e-3),
