@@ -33,12 +33,12 @@ int sympoly(int K, int BK, double *val, double *res, double *overflow) {
   double unit = 1;
   if (B > K) B = K;
   if (B <= 1) B = 2;
-  *overflow = 0;
-  res[0] = 1;
-  for (h = 1; h <= K; h++) res[h] = 0; /* (the reference clears K entries whatever BK is, lib/sympoly.c:74-75) */
-  if (K == 0) return 0;
+  for (h = K; h >= 1; --h) res[h] = 0.0; /* (the reference clears K entries whatever BK is, lib/sympoly.c:74-75) */
+  res[0] = 1.0;
+  *overflow = 0.0;
+  if (K < 1) return 0;
   res[1] = val[0];
-  for (k = 1; k < K; k++) {
+  for (k = 1; k != K; ++k) {
     const double x = val[k];
     apply_factor(res, k + 1 < B ? k + 1 : B, x, unit);
     if (x > 1) {
@@ -48,8 +48,8 @@ int sympoly(int K, int BK, double *val, double *res, double *overflow) {
   }
   if (*overflow < 15) {
     const double back = exp(*overflow);
-    for (h = 1; h <= B; h++) res[h] *= back;
-    *overflow = 0;
+    for (h = B; h >= 1; --h) res[h] *= back;
+    *overflow = 0.0;
   }
   return 0;
 }
@@ -66,7 +66,7 @@ static uint32_t sample_by_table(int K, int H, const double *val, rngp_t rng) {
     if (!tab) return 0;
   }
   tab[0] = val[0];
-  for (k = 1; k < K; k++) {
+  for (k = 1; k != K; ++k) {
     const double x = val[k], *prev = tab + (size_t)(k - 1) * H;
     double *row = tab + (size_t)k * H;
     const int full = k < H ? k : H; /* degrees with an old value */
@@ -79,27 +79,28 @@ static uint32_t sample_by_table(int K, int H, const double *val, rngp_t rng) {
   }
   /* item k stays out with probability F_{k-1,h} / F_{k,h} (same scaling on both sides once a factor x > 1 is
    * put back on the prefix that lacks it) */
-  for (k = K - 1, h = H; k >= h && h > 0; k--) {
+  h = H;
+  for (k = K - 1; h > 0 && k >= h; --k) {
     const double with_k = tab[(size_t)k * H + h - 1], without = tab[(size_t)(k - 1) * H + h - 1];
     if (with_k * rng_unit(rng) >= (val[k] <= 1 ? without : without / val[k])) {
-      chosen |= 1U << (unsigned)k;
-      h--;
+      chosen |= (uint32_t)1 << k;
+      --h;
     }
   }
   if (tab != stack) free(tab);
-  if (h > 0) chosen |= (1U << (unsigned)h) - 1; /* as many items left as are still to be chosen: all of them */
+  if (h > 0) chosen |= ((uint32_t)1 << h) - 1u; /* as many items left as are still to be chosen: all of them */
   return chosen;
 }
 
 uint32_t sympoly_sample(int K, int H, double *val, rngp_t rng) {
   double mass = 0;
-  int k;
-  if (H > K || K == 0 || H == 0) return 0U;
-  if (H == K) return (1U << (unsigned)H) - 1;
-  if (H > 1) return sample_by_table(K, H, val, rng);
+  int k = 0;
+  if (K < 1 || H < 1 || K < H) return 0;
+  if (K == H) return (uint32_t)(((uint64_t)1 << H) - 1);
+  if (H != 1) return sample_by_table(K, H, val, rng);
   /* one item, proportional to its value */
-  for (k = 0; k < K; k++) mass += val[k];
+  while (k != K) mass += val[k++];
   mass *= rng_unit(rng);
-  for (k = 0; k < K && mass > 0; k++) mass -= val[k];
-  return 1U << (unsigned)(k - 1);
+  for (k = 0; mass > 0 && k != K; ++k) mass -= val[k];
+  return (uint32_t)1 << (k - 1);
 }
