@@ -40,7 +40,8 @@ struct stb_table_impl {
    * not free them: it only starts a new epoch, and a block whose epoch is old is fetched again when a
    * look-up next lands in it -- a caller that alternates S_remake and a few look-ups (the samplers' loop,
    * test/demo.c:467-488) pays for the rows it reads, not for pinning and copying the whole table. */
-  unsigned blk_rows, nblk;
+  unsigned blk_rows, nblk; /* blk_rows is a power of two: a scalar look-up finds its block with a shift and a mask */
+  unsigned blk_shift;
   double **blkS, **blkV;
   uint32_t *epochS, *epochV; /* epoch the block's content belongs to (0: never fetched) */
   uint32_t epoch;            /* of the current device content; bumped by every fill */
@@ -95,7 +96,10 @@ static int mirror_reset(stable_t *sp) {
   const size_t ld = stb_cuda_table_ld(im->dev);
   unsigned blk_rows = (unsigned)(MIRROR_BLOCK_BYTES / (ld * sizeof(double)));
   unsigned nblk;
+  unsigned blk_shift = 0;
   if (blk_rows < 1) blk_rows = 1;
+  while ((2u << blk_shift) <= blk_rows) blk_shift++;
+  blk_rows = 1u << blk_shift;
   nblk = (sp->usedN + blk_rows - 1) / blk_rows;
   if (++im->epoch == 0) im->epoch = 1;
   if (ld == im->ld && blk_rows == im->blk_rows && nblk == im->nblk && (!hasS || im->blkS) && (!hasV || im->blkV))
@@ -103,6 +107,7 @@ static int mirror_reset(stable_t *sp) {
   mirror_drop(sp);
   im->ld = ld;
   im->blk_rows = blk_rows;
+  im->blk_shift = blk_shift;
   im->nblk = nblk;
   if (hasS && (!(im->blkS = (double **)calloc(nblk, sizeof(double *))) || !(im->epochS = (uint32_t *)calloc(nblk, sizeof(uint32_t)))))
     return 1;
@@ -143,11 +148,11 @@ static double cell(stable_t *sp, int which, unsigned n, unsigned m) {
   {
     double **tab = which == STB_TAB_S ? im->blkS : im->blkV;
     const uint32_t *ep = which == STB_TAB_S ? im->epochS : im->epochV;
-    const unsigned b = (n - 1) / im->blk_rows;
+    const unsigned b = (n - 1) >> im->blk_shift;
     double *blk = tab[b];
     if (__atomic_load_n(&ep[b], __ATOMIC_ACQUIRE) != im->epoch && !(blk = mirror_fetch(sp, which, b)))
       yaps_quit("stable: device read failed: %s\n", stb_cuda_last_error());
-    v = blk[(size_t)((n - 1) % im->blk_rows) * im->ld + (m - 1)];
+    v = blk[(size_t)((n - 1) & (im->blk_rows - 1)) * im->ld + (m - 1)];
   }
   unlock(sp);
   return v;
