@@ -372,7 +372,11 @@ __device__ __forceinline__ void strip_steps(double (&x)[K], const double (&ma)[K
     // it is the first value the step computes.  (Constant offsets fold into the instructions.)
     if (i > 0) {
 #pragma unroll
+#ifdef STB_EXP_NOSTS  /* timing experiment (wrong results): the producer without 4 of its 5 stores per row */
+      for (int k = 0; k < 0; k++) {
+#else
       for (int k = 0; k < K - 1; k++) {
+#endif
         sts_f64(xr + ((i - 1) * CP + k) * 8, x[k]);
         if (DUP) sts_f64(xr + ((RS + i - 1) * CP + k) * 8, x[k]);
       }
@@ -523,6 +527,9 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
     // batch p overwrites the x-ring rows of batch p - NB/2: the flusher must be done with that one (G == 1);
     // G > 1: the boundary ring holds ST_NBR batches
     const int need_in = has_left ? jb : NO_NEED, need_out = has_right ? p - (OUT ? ST_NBR : NB / 2) : NO_NEED;
+#if defined(STB_EXP_PRODONLY) || defined(STB_EXP_NOGENWAIT)  /* timing experiments (wrong results): the producer never waits for ring slots (PRODONLY: there are no consumers) */
+    gen_next = make_int2(0x3fffffff, 0x3fffffff);
+#endif
     if (gen_next.x < gen_need || gen_next.y < gen_need || c_in < need_in || c_out < need_out) {
 #ifdef STB_PROFILE_PRODUCER
       {  // which condition holds the producer up (cycles attributed to the first one found wanting)
@@ -799,7 +806,14 @@ __device__ void strip_consumer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
     const bool tri = r0 < cvalid;
     if (tri && r0 + ST_RB <= 32 * kk) {
       // (every cell of the unit is above the diagonal)
+#ifdef STB_EXP_NOCONS  /* timing experiment (wrong results): consumers release their units without touching them */
+    } else if (true) {
+#endif
+#if !defined(STB_EXP_NOCONS)
     } else if (r0 <= r_fast_hi) {
+#else
+    } else if (false) {
+#endif
       // (tried: a variant for strips whose consumers are a multiple of the column blocks -- every warp keeps its
       // block, the column's geometry hoisted out of the loop: 4 % SLOWER on config 2, 9.44 against 9.04 ms)
       const int col = lane + 32 * kk;
@@ -1159,7 +1173,11 @@ __device__ __forceinline__ void cta_roles(StripSmem<K, G, HAS_V> &sm, const Stri
     int ncs = (ntot - gi + G - 1) / G;
     if (ncs > Cfg::NB - 1) ncs = Cfg::NB - 1;
     if (ncs > P.ncons) ncs = P.ncons;
+#ifdef STB_EXP_PRODONLY
+    if (false) {
+#else
     if (gi < nloc && ci < ncs) {
+#endif
       const StripGeom g = strip_geom(P, strip0 + gi);
       const unsigned ltab = smem_u32(sm.logtab + (lane & (LOGTAB_REP8 - 1))) - LOGTAB_IDX0 * (LOGTAB_REP8 * 8);
       if (g.rs == 0)
