@@ -547,6 +547,18 @@ __device__ void strip_producer(const StripParams &P, StripSub<K, G, HAS_V> &sb, 
       c_out = max(c_out, need_out);
     }
     ST_TICK(tk2);
+#ifdef STB_PROFILE_TRACE
+    if (p < 24 && lane0 && P.dbg && blockIdx.x < 4) {  // start of each of the strip's first batches, ns since the kernel's start
+      unsigned long long gt_now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_now));
+      P.dbg[900 * 8 + blockIdx.x * 24 + p] = (long long)(gt_now - gt_start);
+    }
+    if (p >= g.nbatch - 24 && lane0 && P.dbg && blockIdx.x < 4) {  // ... and of its last ones
+      unsigned long long gt_now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_now));
+      P.dbg[900 * 8 + 96 + blockIdx.x * 24 + (p - (g.nbatch - 24))] = (long long)(gt_now - gt_start);
+    }
+#endif
 #ifdef STB_PROFILE_PRODUCER
     if (p == 0) {  // when the strip's first batch starts (its input has arrived), ns since the kernel's start
       unsigned long long gt_now;
@@ -1512,6 +1524,16 @@ inline int strip_fill(StripState *st, const StripFillArgs &A, cudaStream_t strea
                       (double)d[0] / d[3], (double)d[1] / d[3], (double)d[2] / d[3]);
           }
         }
+#ifdef STB_PROFILE_TRACE
+        for (int c = 0; c < 4; c++) {
+          fprintf(stderr, "cta %d first batches start at (us):", c);
+          for (int b = 0; b < 24; b++) fprintf(stderr, " %.2f", h[900 * 8 + c * 24 + b] / 1e3);
+          fprintf(stderr, "\n");
+          fprintf(stderr, "cta %d last batches start at (us):", c);
+          for (int b = 0; b < 24; b++) fprintf(stderr, " %.2f", h[900 * 8 + 96 + c * 24 + b] / 1e3);
+          fprintf(stderr, "\n");
+        }
+#endif
         const int show[10] = {0, 1, 2, 3, nctas / 4, nctas / 2, nctas / 2 + 1, 3 * nctas / 4, nctas - 2, nctas - 1};
         for (int si = 0; si < 10; si++) {
           const int c = show[si];
